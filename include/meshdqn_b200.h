@@ -1,0 +1,191 @@
+/*
+ * meshdqn_b200.h -- C ABI of libmeshdqn_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (BaratiLab/MeshDQN) is pure Python with no FFI; its "plugin
+ * boundary" for the hot path is the Python surface of airfoilgcnn.py and
+ * Env2DAirfoil.py, whose arithmetic lives in torch_geometric / DOLFIN / shapely.
+ * Each entry point below replaces one of those third-party call sites; the
+ * Python host mirror (meshdqn_b200/*.py) keeps the reference's class and method
+ * names and calls these through ctypes.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller unless its name starts
+ *     with h_ (host); the callee never allocates, frees or retains them;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no internal
+ *     synchronisation, re-entrant per stream;
+ *   - return 0 on success, a negative MDQ_E* code on failure (never throws);
+ *     mdq_last_error() gives a thread-local message.
+ */
+#ifndef MESHDQN_B200_H
+#define MESHDQN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDQ_OK 0
+#define MDQ_EINVAL (-1)   /* bad argument / unsupported size */
+#define MDQ_ECUDA (-2)    /* CUDA runtime error (see mdq_last_error) */
+#define MDQ_ESMEM (-3)    /* problem does not fit the fused kernel's shared memory */
+
+#define MDQ_MAX_BLOCKS 6
+#define MDQ_BLOCK_SAGE 0
+#define MDQ_BLOCK_GCN 1
+
+const char *mdq_last_error(void);
+int mdq_version(void);
+/* number of kernel launches issued through this library by the calling process */
+int64_t mdq_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Q-network (replaces torch_geometric SAGEConv/GCNConv/TopKPooling/global pools +
+ * nn.Linear/softmax/argmax in /root/reference/airfoilgcnn.py:85-145 and :170-209).
+ *
+ * All parameters live in ONE flat fp32 buffer; offsets are in floats.  Dense weights are
+ * stored transposed ([in][out], out contiguous) so a warp reads consecutive outputs:
+ *   SAGE block: w_off -> [2*kin][width]  rows 0..kin-1 = lin_l.weight^T, kin..2kin-1 = lin_r.weight^T
+ *               b_off -> lin_l.bias [width]
+ *   GCN  block: w_off -> [kin][width] = lin.weight^T ; b_off -> bias [width]
+ *   pool_off -> TopKPooling.weight [width]
+ *   lin_off[i] -> [lin_in[i]][lin_out[i]] = lin{i+1}.weight^T ; lin_boff[i] -> bias
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t type;      /* MDQ_BLOCK_SAGE | MDQ_BLOCK_GCN */
+    int32_t kin;       /* input features of this block */
+    int32_t w_off, b_off, pool_off;
+} mdq_block_t;
+
+typedef struct {
+    int32_t n_blocks;
+    int32_t width;        /* conv_width (multiple of 4, <= 256) */
+    int32_t in_dim;       /* features the first block consumes */
+    int32_t in_col0;      /* first used column of data.x (AirfoilGCNN: x[:, [2,3]] -> 2) */
+    int32_t x_stride;     /* columns of data.x */
+    float ratio;          /* TopKPooling ratio */
+    int32_t softmax;      /* 1: softmax over the last layer (NodeRemovalNet), 0: raw (AirfoilGCNN) */
+    int32_t out_dim;
+    int32_t lin_off[3], lin_boff[3], lin_in[3], lin_out[3];
+    int32_t n_params;     /* floats in the flat buffer */
+    mdq_block_t blk[MDQ_MAX_BLOCKS];
+} mdq_net_t;
+
+/* Shared memory (bytes) the fused kernels need for graphs of at most max_n nodes / max_e edges
+ * with `gpc` graphs per CTA; backward != 0 for the recompute+backward kernel.  Host-callable, no GPU. */
+int64_t mdq_qnet_smem_bytes(const mdq_net_t *net, int max_n, int max_e, int gpc, int backward);
+/* graphs per CTA the forward launch will use for this batch (host-callable) */
+int mdq_qnet_pick_gpc(const mdq_net_t *net, int n_graphs, int max_n, int max_e);
+
+/* Forward: one CTA per `gpc` graphs.
+ *   x [sum_n, x_stride] f32; edge_src/edge_dst [sum_e] i64 GLOBAL node ids (PyG edge_index rows 0/1);
+ *   node_ptr / edge_ptr [B+1] i32.  out [B, out_dim] f32 (softmax "Q-values");
+ *   embedding (nullable) [B, 2*width]; argmax (nullable) [B] i32 (first maximum). */
+int mdq_qnet_forward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                     const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                     int max_n, int max_e, float *out, float *embedding, int32_t *argmax, void *stream);
+
+/* Rows of (delta, input) pairs the backward kernel emits for the weight-gradient pass. */
+int64_t mdq_qnet_bwd_workspace_floats(const mdq_net_t *net, int n_graphs, int max_n);
+
+/* Backward (recomputes the forward per graph, deterministic, atomics-free):
+ *   grad_out [B, out_dim] = dL/d out.  Writes the flat gradient grad [n_params] (overwritten).
+ *   workspace: mdq_qnet_bwd_workspace_floats() floats. */
+int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                      const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                      int max_n, int max_e, const float *grad_out, float *grad, float *workspace, void *stream);
+
+/* Replay-minibatch loss (replaces /root/reference/airfoil_dqn.py:264,267-283,303-304):
+ *   pred_b = q1[b, action[b]];  target_b = reward[b] + gamma * (nonfinal[b] ? max_a q2[slot[b], a] : 0)
+ *   loss = mean_b huber(pred_b - target_b, delta = 1)
+ * select != 0: grad_q1 [B, A] = dloss/dq1 (grad_q2 untouched); select == 0: grad_q2 [B2, A] = dloss/dq2.
+ * next_slot[b] = row of q2 holding b's next state, or -1 when the transition is terminal. */
+int mdq_huber_replay(const float *q1, const float *q2, const int32_t *action, const float *reward,
+                     const int32_t *next_slot, int batch, int n_next, int out_dim, float gamma, int select,
+                     float *loss, float *grad_q1, float *grad_q2, void *stream);
+
+/* Adam step on flat buffers with torch.optim.Adam semantics (L2 weight decay added to the gradient;
+ * /root/reference/airfoil_dqn.py:172-173).  grad is multiplied by grad_scale first (1/world_size after
+ * an all-reduce sum).  step is the 1-based step count. */
+int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
+                  void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Environment step, float64 geometry (replaces DOLFIN / shapely calls in
+ * /root/reference/Env2DAirfoil.py and flow_solver.py).  Coordinates are [n,2] f64 row-major,
+ * cells [n,3] i32 with ascending vertex ids per cell (DOLFIN's ordering after close()).
+ * ------------------------------------------------------------------------------------ */
+
+/* Exclusive scan of int32 in[0..n) -> out[0..n] (out[n] = total); one CTA, stream-ordered. */
+int mdq_scan_i32(const int32_t *in, int32_t *out, int n, void *stream);
+
+/* Mesh topology (replaces Mesh.init / BoundaryMesh, flow_solver.py:75,247; Env2DAirfoil.py:464).
+ * Deterministic and sort-free: per-vertex sorted neighbour lists give lexicographic edge ids.
+ *   nbr_ptr [nv+1], nbr_idx [6*nc] ascending neighbours; vc_ptr [nv+1], vc_idx [3*nc] ascending cells;
+ *   edge_base [nv+1] (edges owned by their lower endpoint), edges [3*nc,2] (first ne rows valid),
+ *   cell_edges [nc,3] (edge opposite local vertex i), edge_ncells [3*nc], edge_cell [3*nc] = 4*cell+local for
+ *   exterior facets, on_boundary [nv] u8, bverts [nv] (ascending boundary vertex ids),
+ *   counts int32[4]: [0] = ne, [1] = #boundary vertices, [3] = 1 if a vertex exceeded the neighbour capacity.
+ *   scratch: int32 [2*nv + 2]. */
+int mdq_mesh_topology(const int32_t *cells, int nc, int nv, int32_t *nbr_ptr, int32_t *nbr_idx, int32_t *vc_ptr,
+                      int32_t *vc_idx, int32_t *edge_base, int32_t *edges, int32_t *cell_edges, int32_t *edge_ncells,
+                      int32_t *edge_cell, uint8_t *on_boundary, int32_t *bverts, int32_t *counts, int32_t *scratch,
+                      void *stream);
+
+/* Mesh.smooth(iters) (flow_solver.py:67,237): in-place Gauss-Seidel sweep in vertex order, boundary fixed.
+ * The exact sweep order is kept by level-scheduling the vertex dependency DAG inside one CTA.
+ * level [nv] i32 scratch. */
+int mdq_mesh_smooth(double *coords, int nv, const int32_t *nbr_ptr, const int32_t *nbr_idx, const int32_t *vc_ptr,
+                    const int32_t *vc_idx, const int32_t *cells, const uint8_t *on_boundary, int iters, int32_t *level,
+                    void *stream);
+
+/* FlowSolver.mark_boundaries (flow_solver.py:9-30,194-226): tags [ne] i32 (4 default, 0 walls, 1 airfoil,
+ * 2 inflow, 3 outflow) and the removable mask (flow_solver.py:75-78,247-250; numpy `coord not in B`) [nv] u8. */
+int mdq_mesh_tags_removable(const double *coords, int nv, const int32_t *edges, const int32_t *edge_ncells, int ne,
+                            const int32_t *bverts, int nb, int32_t *tags, uint8_t *removable, void *stream);
+
+/* shapely Polygon.distance(Point) (Env2DAirfoil.py:232,240-241): dist[i] for points coords[idx[i]]
+ * (idx nullable = identity) against the closed ring [nr,2]. */
+int mdq_polygon_distance(const double *coords, const int32_t *idx, int np, const double *ring, int nr, double *dist,
+                         void *stream);
+
+/* Uniform-grid index over the SOURCE mesh M0 for point location.  h_grid (HOST, 6 doubles):
+ * x0, y0, 1/dx, 1/dy, gx, gy.  mdq_grid_count -> bin_cnt [gx*gy+1] (entries per bin); the caller scans it
+ * (mdq_scan_i32) into bin_ptr and sizes bin_cells = bin_ptr[gx*gy]; mdq_grid_fill writes the cell lists. */
+int mdq_grid_count(const double *coords0, const int32_t *cells0, int nc0, const double *h_grid, int32_t *bin_cnt,
+                   void *stream);
+int mdq_grid_fill(const double *coords0, const int32_t *cells0, int nc0, const double *h_grid,
+                  const int32_t *bin_ptr, int32_t *bin_cursor, int32_t *bin_cells, void *stream);
+
+/* Function.interpolate for T snapshots (Env2DAirfoil.py:556-568, :515-522):
+ *   target P2 dof points = vertices [nv] then edge midpoints 0.5*a+0.5*b [ne];
+ *   located in M0: lowest-index cell with min barycentric >= -tol, else the closest cell (lowest index on ties);
+ *   U0 [T][nv0+ne0][2], P0 [T][nv0]  ->  U [T][nv+ne][2], P [T][nv], cell_of [nv+ne] i32.
+ *   miss_count: device int32 (points that needed the closest-cell fallback); miss_list [nv+ne] scratch. */
+int mdq_interpolate(const double *coords, int nv, const int32_t *edges, int ne, const double *coords0,
+                    const int32_t *cells0, const int32_t *cell_edges0, int nv0, int ne0, int nc0,
+                    const double *h_grid, const int32_t *bin_ptr, const int32_t *bin_cells, double tol, int T,
+                    const double *U0, const double *P0, double *U, double *P, int32_t *cell_of,
+                    int32_t *miss_count, int32_t *miss_list, void *stream);
+
+/* DragProbe/LiftProbe.sample for T <= 8 snapshots (probes.py:23-31,43-50): sum over exterior facets with
+ * tag == 1 of |f| (sigma(m_f) n).e_x / e_y.  drag_lift [2][T] f64.  Deterministic fixed-shape reduction. */
+int mdq_drag_lift(const double *coords, const int32_t *cells, const int32_t *cell_edges, int nv, int ne,
+                  const int32_t *tags, const int32_t *edge_cell, int T, const double *U, const double *P, double mu,
+                  double *drag_lift, void *stream);
+
+/* Env2DAirfoil.get_state (Env2DAirfoil.py:244-315) on device, quirks B1-B3 included:
+ *   dist [nrem] f64 distances of the removable vertices (list order), removable_idx [nrem] i32;
+ *   picks order[offset : offset+N] of the stable ascending argsort -> n_closest [N] (positions in the
+ *   removable list, -1 when out of vertices), coord_map [N], inv_map [nv]; x [N, 3T+2] f32;
+ *   edge_index i64 [2][ecap] (PyG layout, first n_edges columns valid). */
+int mdq_build_state(const double *dist, const int32_t *removable_idx, int nrem, int offset, int N,
+                    const double *coords, int nv, const int32_t *cells, int nc, int T, const double *U, int np2,
+                    const double *P, int32_t *n_closest, int32_t *coord_map, int32_t *inv_map, float *x,
+                    int64_t *edge_index, int ecap, int32_t *n_edges, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHDQN_B200_H */

@@ -1,0 +1,1152 @@
+// gnn_fused.cu -- fused Q-network kernels (sm_100a).
+//
+// Replaces the torch_geometric call sites of /root/reference/airfoilgcnn.py:85-145 (NodeRemovalNet.forward)
+// and :170-209 (AirfoilGCNN.forward): SAGEConv / GCNConv message passing, TopKPooling, global max/mean
+// readout, the 3-layer MLP, softmax and the argmax of airfoil_dqn.py:209 -- in ONE kernel launch, one CTA
+// per `gpc` graphs, every intermediate in shared memory.  The backward kernel recomputes the forward per
+// graph (nothing is saved between launches), back-propagates through the kept rows only (TopK makes every
+// other row's gradient zero) and emits (delta, input) rows; a split-K weight-gradient pass reduces them in
+// a fixed order, so gradients are deterministic and atomics-free.
+//
+// Message passing is a stable CSR-by-destination gather (edges keep their edge_index order inside a row,
+// as torch_scatter's CPU loop does), mean / GCN-normalised, fp32, sequential per row.
+#include <math.h>
+#include <string.h>
+
+#include "mdq_common.cuh"
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int NWARP = NT / 32;
+constexpr int MAXB = MDQ_MAX_BLOCKS;
+constexpr int MLP_SPLIT = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct QLay {
+    int G, n_max, e_max, KC1, W, nb, bwd;
+    int ncap[MAXB + 1];    // per-graph row cap entering block b; ncap[nb] = rows after the last pool
+    int rowoff[MAXB + 1];  // b>=1: first row (in xbuf / per-row arrays) of block b's input rows
+    int hoff[MAXB + 1];    // b>=1: first row in hbuf of block b's hidden rows
+    int eoff[MAXB + 1];    // b>=1: offset of block b's edge list in e2s/e2d
+    int xrows, e2cap, nrow_all, ymax;
+    int o_w1, o_cat1, o_big, o_cat2, o_xbuf, o_hbuf, o_e1s, o_e1d, o_csr, o_e2s, o_e2d;
+    int o_rowptr, o_cursor, o_score, o_z, o_newid, o_parent, o_dis, o_seg, o_ecnt, o_racc, o_y, o_part;
+    int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds;
+    int total;  // 4-byte words
+};
+
+struct WLayer {
+    int K, C, rpg, w_off, b_off, d_off, i_off;
+};
+constexpr int MAXWL = 3 * MAXB + 3;
+struct WDesc {
+    int nl;
+    int total;  // floats of workspace
+    WLayer l[MAXWL];
+};
+
+struct QArgs {
+    mdq_net_t net;
+    QLay L;
+    const float *params;
+    const float *x;
+    const long long *esrc, *edst;  // int64 edge_index rows (PyG layout)
+    const int *nptr, *eptr;
+    int B;
+    float *out, *emb;
+    int *amax_out;
+    const float *gout;
+    float *ws;
+    WDesc wd;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host: shared-memory layout
+// ------------------------------------------------------------------------------------------------
+int topk_count(float ratio, int n) { return (int)ceilf(ratio * (float)n); }
+
+int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLay &L)
+{
+    memset(&L, 0, sizeof(L));
+    if (net.n_blocks < 1 || net.n_blocks > MAXB) return MDQ_EINVAL;
+    if (net.width < 4 || net.width > 256 || (net.width & 3)) return MDQ_EINVAL;
+    if (net.blk[0].type != MDQ_BLOCK_SAGE || net.blk[0].kin != net.in_dim) return MDQ_EINVAL;
+    for (int b = 1; b < net.n_blocks; ++b)
+        if (net.blk[b].kin != net.width) return MDQ_EINVAL;
+    if (net.lin_in[0] != 2 * net.width || net.lin_in[1] != net.lin_out[0] || net.lin_in[2] != net.lin_out[1] ||
+        net.lin_out[2] != net.out_dim)
+        return MDQ_EINVAL;
+    for (int i = 0; i < 3; ++i)
+        if (net.lin_in[i] % MLP_SPLIT) return MDQ_EINVAL;
+    if (max_n < 1 || max_e < 0 || G < 1) return MDQ_EINVAL;
+    if (bwd && G != 1) return MDQ_EINVAL;
+    const int W = net.width, nb = net.n_blocks;
+    L.G = G; L.n_max = max_n; L.e_max = max_e > 0 ? max_e : 1; L.W = W; L.nb = nb; L.bwd = bwd;
+    L.KC1 = mdq::pad4(2 * net.in_dim);
+    L.ncap[0] = max_n;
+    for (int b = 0; b < nb; ++b) L.ncap[b + 1] = topk_count(net.ratio, L.ncap[b]);
+    const int gcap1 = G * L.ncap[1];
+    if (bwd) {
+        int r = 0;
+        for (int b = 1; b <= nb; ++b) { L.rowoff[b] = r; L.hoff[b] = r; r += G * L.ncap[b]; }
+        L.xrows = r;
+        for (int b = 1; b < nb; ++b) L.eoff[b] = (b - 1) * G * L.e_max;
+        L.e2cap = (nb > 1 ? nb - 1 : 1) * G * L.e_max;
+    } else {
+        for (int b = 1; b <= nb; ++b) { L.rowoff[b] = ((b - 1) & 1) * gcap1; L.hoff[b] = 0; }
+        L.xrows = 2 * gcap1;
+        for (int b = 1; b < nb; ++b) L.eoff[b] = ((b - 1) & 1) * G * L.e_max;
+        L.e2cap = 2 * G * L.e_max;
+    }
+    L.nrow_all = max_n + L.xrows;
+    int ymax = net.lin_out[0];
+    if (net.lin_out[1] > ymax) ymax = net.lin_out[1];
+    if (net.out_dim > ymax) ymax = net.out_dim;
+    L.ymax = mdq::pad4(ymax);
+    int o = 0;
+    auto take = [&](int words) { int at = o; o += mdq::pad4(words); return at; };
+    L.o_w1 = take((L.KC1 + 1) * W);
+    L.o_cat1 = take(max_n * L.KC1);
+    const int big_fwd = max_n * W > gcap1 * 2 * W ? max_n * W : gcap1 * 2 * W;
+    L.o_big = take(bwd ? max_n * W : big_fwd);
+    L.o_cat2 = bwd ? take(gcap1 * 2 * W) : L.o_big;
+    L.o_xbuf = take(L.xrows * W);
+    L.o_hbuf = take((bwd ? L.xrows : gcap1) * W);
+    L.o_e1s = take(L.e_max);
+    L.o_e1d = take(L.e_max);
+    L.o_csr = take(G * L.e_max);
+    L.o_e2s = take(L.e2cap);
+    L.o_e2d = take(L.e2cap);
+    const int rmax = max_n > gcap1 ? max_n : gcap1;
+    L.o_rowptr = take(rmax + 2);
+    L.o_cursor = take(rmax + 2);
+    L.o_score = take(L.nrow_all);
+    L.o_z = take(L.nrow_all);
+    L.o_newid = take(L.nrow_all);
+    L.o_parent = take(L.nrow_all);
+    L.o_dis = take(rmax);
+    L.o_seg = take((nb + 1) * (G + 1));
+    L.o_ecnt = take(nb + 1);
+    L.o_racc = take(G * 2 * W);
+    L.o_y = take(G * 3 * L.ymax);
+    L.o_part = take(MLP_SPLIT * G * L.ymax);
+    if (bwd) {
+        L.o_dx = take(L.xrows * W);
+        L.o_dp = take(gcap1 * W);
+        const int a = G * L.ncap[nb > 1 ? 2 : 1] * 2 * W, c = gcap1 * W;
+        L.o_dcat = take(a > c ? a : c);
+        L.o_dr = take(2 * W + 3 * L.ymax);
+        L.o_amax = take(nb * G * W);
+        L.o_tds = take(gcap1 * 2);
+    }
+    L.total = o;
+    return MDQ_OK;
+}
+
+int build_wdesc(const mdq_net_t &net, int B, int max_n, WDesc &wd)
+{
+    memset(&wd, 0, sizeof(wd));
+    int ncap[MAXB + 1];
+    ncap[0] = max_n;
+    for (int b = 0; b < net.n_blocks; ++b) ncap[b + 1] = topk_count(net.ratio, ncap[b]);
+    int nl = 0, off = 0;
+    auto add = [&](int K, int C, int rpg, int w_off, int b_off) {
+        WLayer &l = wd.l[nl++];
+        l.K = K; l.C = C; l.rpg = rpg; l.w_off = w_off; l.b_off = b_off;
+        l.d_off = off; off += mdq::pad4(B * rpg * C);
+        l.i_off = off; off += mdq::pad4(B * rpg * K);
+    };
+    const int W = net.width;
+    for (int b = 0; b < net.n_blocks; ++b) {  // layers [0, nb): conv weights
+        const mdq_block_t &k = net.blk[b];
+        if (k.type == MDQ_BLOCK_SAGE) add(2 * k.kin, W, ncap[b + 1], k.w_off, k.b_off);
+        else add(k.kin, W, ncap[b], k.w_off, -1);
+    }
+    for (int b = 0; b < net.n_blocks; ++b) add(0, W, 1, -1, net.blk[b].pool_off);  // [nb, 2nb): pool weights
+    for (int i = 0; i < 3; ++i) add(net.lin_in[i], net.lin_out[i], 1, net.lin_off[i], net.lin_boff[i]);  // [2nb, 2nb+3)
+    for (int b = 0; b < net.n_blocks; ++b)  // [2nb+3, 3nb+3): GCN bias (K=0), unused (rpg=0) for SAGE
+        add(0, W, net.blk[b].type == MDQ_BLOCK_GCN ? 1 : 0, -1, net.blk[b].b_off);
+    wd.nl = nl;
+    wd.total = off;
+    return MDQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int topk_count_dev(float ratio, int n) { return __float2int_ru(__fmul_rn(ratio, (float)n)); }
+
+// Stable CSR by destination: rowptr[n+1], csr[E] = source of each in-edge, in edge_index order per row.
+__device__ void build_csr(int n, int E, const int *es, const int *ed, int *rowptr, int *cursor, int *csr)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= n; i += NT) cursor[i] = 0;
+    __syncthreads();
+    for (int e = tid; e < E; e += NT) atomicAdd(&cursor[ed[e]], 1);
+    __syncthreads();
+    if (tid < 32) {
+        int carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + tid;
+            const int v = (i < n) ? cursor[i] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += t;
+            }
+            if (i < n) rowptr[i] = carry + incl - v;
+            carry += __shfl_sync(FULL, incl, 31);
+        }
+        if (tid == 0) rowptr[n] = carry;
+        __syncwarp();
+        for (int i = tid; i < n; i += 32) cursor[i] = rowptr[i];
+        __syncwarp();
+        for (int base = 0; base < E; base += 32) {
+            const int e = base + tid;
+            const bool valid = e < E;
+            const int d = valid ? ed[e] : (-1 - tid);
+            const unsigned m = __match_any_sync(FULL, d);
+            const int rank = __popc(m & ((1u << tid) - 1u));
+            const int pos = valid ? cursor[d] + rank : 0;
+            __syncwarp();
+            if (valid && (31 - __clz(m)) == tid) cursor[d] += __popc(m);
+            __syncwarp();
+            if (valid) csr[pos] = es[e];
+        }
+    }
+    __syncthreads();
+}
+
+// out[r][c] = act(bias[c] + sum_k A[r][k] * WT[k][c]); 4x4 register tile, k ascending.
+template <bool W_SMEM>
+__device__ void dense_rows(int n, int K, const float *A, int lda, const float *WT, const float *bias, float *out,
+                           int ldo, int W, bool relu)
+{
+    const int q = W >> 2;
+    const int ngroups = (n + 3) >> 2;
+    for (int item = threadIdx.x; item < ngroups * q; item += NT) {
+        const int rg = item / q;
+        const int c4 = (item - rg * q) << 2;
+        const int r0 = rg << 2;
+        const float *a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
+        float acc[4][4];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b4 = W_SMEM ? *reinterpret_cast<const float4 *>(bias + c4)
+                              : __ldg(reinterpret_cast<const float4 *>(bias + c4));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+#pragma unroll 2
+        for (int k = 0; k < K; k += 4) {
+            float4 w[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                w[kk] = W_SMEM ? *reinterpret_cast<const float4 *>(WT + (size_t)(k + kk) * W + c4)
+                               : __ldg(reinterpret_cast<const float4 *>(WT + (size_t)(k + kk) * W + c4));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 xv = *reinterpret_cast<const float4 *>(a[j] + k);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    acc[j][0] = fmaf(xs[kk], w[kk].x, acc[j][0]);
+                    acc[j][1] = fmaf(xs[kk], w[kk].y, acc[j][1]);
+                    acc[j][2] = fmaf(xs[kk], w[kk].z, acc[j][2]);
+                    acc[j][3] = fmaf(xs[kk], w[kk].w, acc[j][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (r0 + j < n) {
+                float4 o4 = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+                *reinterpret_cast<float4 *>(out + (size_t)(r0 + j) * ldo + c4) = o4;
+            }
+        }
+    }
+}
+
+// rows x K times WT[K][O] (+ bias), split-K over MLP_SPLIT slices combined in slice order.
+__device__ void mlp_layer(int rows, int K, int O, const float *in, int ldi, const float *__restrict__ WT,
+                          const float *__restrict__ b, float *out, int ldo, bool relu, float *part)
+{
+    const int RO = rows * O;
+    const int Ks = K / MLP_SPLIT;
+    for (int item = threadIdx.x; item < MLP_SPLIT * RO; item += NT) {
+        const int s = item / RO;
+        const int rem = item - s * RO;
+        const int r = rem / O, c = rem - r * O;
+        const float *xi = in + r * ldi + s * Ks;
+        const float *wp = WT + (size_t)(s * Ks) * O + c;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < Ks; ++k) acc = fmaf(xi[k], __ldg(wp + (size_t)k * O), acc);
+        part[item] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < RO; idx += NT) {
+        const int r = idx / O, c = idx - r * O;
+        float v = __ldg(b + c);
+#pragma unroll
+        for (int s = 0; s < MLP_SPLIT; ++s) v += part[s * RO + idx];
+        out[r * ldo + c] = relu ? fmaxf(v, 0.f) : v;
+    }
+    __syncthreads();
+}
+
+// v[k] = sum_c d[c] * WT[k][c]  (one warp per k, lanes over c; used for input gradients)
+__device__ void matvec_t(int K, int C, const float *d, const float *__restrict__ WT, float *v, const float *gate)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < K; k += NWARP) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(d[c], __ldg(WT + (size_t)k * C + c), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) v[k] = (gate == nullptr || gate[k] > 0.f) ? acc : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused kernel
+// ------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    const QLay &L = a.L;
+    const mdq_net_t &net = a.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = L.W, nb = L.nb, G = L.G, KC1 = L.KC1, F = net.in_dim;
+    const int g0 = blockIdx.x * G;
+    const int ng = min(G, a.B - g0);
+    if (ng <= 0) return;
+
+    float *w1s = smem + L.o_w1;
+    float *cat1 = smem + L.o_cat1;
+    float *big = smem + L.o_big;
+    float *cat2 = smem + L.o_cat2;
+    float *xbuf = smem + L.o_xbuf;
+    float *hbuf = smem + L.o_hbuf;
+    int *e1s = reinterpret_cast<int *>(smem + L.o_e1s);
+    int *e1d = reinterpret_cast<int *>(smem + L.o_e1d);
+    int *csr = reinterpret_cast<int *>(smem + L.o_csr);
+    int *e2s = reinterpret_cast<int *>(smem + L.o_e2s);
+    int *e2d = reinterpret_cast<int *>(smem + L.o_e2d);
+    int *rowptr = reinterpret_cast<int *>(smem + L.o_rowptr);
+    int *cursor = reinterpret_cast<int *>(smem + L.o_cursor);
+    float *score = smem + L.o_score;
+    float *zval = smem + L.o_z;
+    int *newid = reinterpret_cast<int *>(smem + L.o_newid);
+    int *parent = reinterpret_cast<int *>(smem + L.o_parent);
+    float *dis = smem + L.o_dis;
+    int *seg = reinterpret_cast<int *>(smem + L.o_seg);  // [nb+1][G+1]
+    int *ecnt = reinterpret_cast<int *>(smem + L.o_ecnt);
+    float *racc = smem + L.o_racc;
+    float *ybuf = smem + L.o_y;
+    float *part = smem + L.o_part;
+    int *amaxs = BWD ? reinterpret_cast<int *>(smem + L.o_amax) : nullptr;
+
+    const float *P = a.params;
+
+    // ---- stage conv1 weights (+bias row) in shared memory, zero padded to KC1 rows ----
+    {
+        const float *wg = P + net.blk[0].w_off;
+        const int rows = 2 * F;
+        for (int idx = tid; idx < KC1 * W; idx += NT) w1s[idx] = (idx < rows * W) ? __ldg(wg + idx) : 0.f;
+        for (int c = tid; c < W; c += NT) w1s[KC1 * W + c] = __ldg(P + net.blk[0].b_off + c);
+        if (tid <= G) seg[1 * (G + 1) + tid] = 0;
+        if (tid <= nb) ecnt[tid] = 0;
+    }
+    __syncthreads();
+
+    // pool weight norm helper: each warp recomputes it (W <= 256 -> <= 8 values per lane)
+    auto pool_weights = [&](int b, float (&pw)[8], float &wnorm) {
+        const float *wp = P + net.blk[b].pool_off;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            pw[j] = (c < W) ? __ldg(wp + c) : 0.f;
+            ss = fmaf(pw[j], pw[j], ss);
+        }
+        wnorm = sqrtf(warp_sum(ss));
+    };
+
+    // scores of `n` rows H[i][:] -> score/z at per-row index base+i
+    auto compute_scores = [&](int b, int n, const float *H, int base) {
+        float pw[8], wnorm;
+        pool_weights(b, pw, wnorm);
+        for (int i = warp; i < n; i += NWARP) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (c < W) acc = fmaf(H[(size_t)i * W + c], pw[j], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const float z = acc / wnorm;
+                zval[base + i] = z;
+                score[base + i] = tanhf(z);
+            }
+        }
+    };
+
+    // ordered compaction of kept edges (both endpoints kept), ids mapped through newid (+base of the row arrays)
+    auto filter_edges = [&](int E, const int *es, const int *ed, int nbase, int *os, int *od, int *count) {
+        if (warp == 0) {
+            int cnt = *count;
+            for (int base = 0; base < E; base += 32) {
+                const int e = base + lane;
+                const bool valid = e < E;
+                const int s = valid ? newid[nbase + es[e]] : -1;
+                const int d = valid ? newid[nbase + ed[e]] : -1;
+                const bool keep = valid && s >= 0 && d >= 0;
+                const unsigned m = __ballot_sync(FULL, keep);
+                if (keep) {
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                    os[pos] = s;
+                    od[pos] = d;
+                }
+                cnt += __popc(m);
+            }
+            __syncwarp();
+            if (lane == 0) *count = cnt;
+        }
+    };
+
+    // ================================ block 0: one graph at a time ================================
+    for (int gi = 0; gi < ng; ++gi) {
+        const int g = g0 + gi;
+        const int nb0 = a.nptr[g], n = a.nptr[g + 1] - nb0;
+        const int eb0 = a.eptr[g], E = a.eptr[g + 1] - eb0;
+        {
+            const float *xg = a.x + (size_t)nb0 * net.x_stride + net.in_col0;
+            for (int idx = tid; idx < n * F; idx += NT) {
+                const int i = idx / F, f = idx - i * F;
+                cat1[i * KC1 + F + f] = __ldg(xg + (size_t)i * net.x_stride + f);
+            }
+            const int padc = KC1 - 2 * F;
+            for (int idx = tid; idx < n * padc; idx += NT) {
+                const int i = idx / padc, f = idx - i * padc;
+                cat1[i * KC1 + 2 * F + f] = 0.f;
+            }
+            for (int e = tid; e < E; e += NT) {
+                e1s[e] = (int)(a.esrc[eb0 + e] - nb0);
+                e1d[e] = (int)(a.edst[eb0 + e] - nb0);
+            }
+        }
+        __syncthreads();
+        build_csr(n, E, e1s, e1d, rowptr, cursor, csr);
+        for (int idx = tid; idx < n * F; idx += NT) {  // mean aggregation, edge order per row
+            const int i = idx / F, f = idx - i * F;
+            const int s0 = rowptr[i], s1 = rowptr[i + 1];
+            float sum = 0.f;
+            for (int s = s0; s < s1; ++s) sum += cat1[csr[s] * KC1 + F + f];
+            const int cnt = s1 - s0;
+            cat1[i * KC1 + f] = sum / (float)(cnt > 0 ? cnt : 1);
+        }
+        __syncthreads();
+        dense_rows<true>(n, KC1, cat1, KC1, w1s, w1s + KC1 * W, big, W, W, true);
+        __syncthreads();
+        compute_scores(0, n, big, 0);
+        __syncthreads();
+        const int k = topk_count_dev(net.ratio, n);
+        const int obase = seg[1 * (G + 1) + gi];
+        for (int i = tid; i < n; i += NT) {
+            const float si = score[i];
+            int r = 0;
+            for (int j = 0; j < n; ++j) {
+                const float sj = score[j];
+                r += (sj > si) || (sj == si && j < i);
+            }
+            newid[i] = (r < k) ? (obase + r) : -1;
+            if (r < k) parent[L.n_max + L.rowoff[1] + obase + r] = i;
+        }
+        if (tid == 0) seg[1 * (G + 1) + gi + 1] = obase + k;
+        __syncthreads();
+        {
+            float *xo = xbuf + (size_t)(L.rowoff[1] + obase) * W;
+            const int *par = parent + L.n_max + L.rowoff[1] + obase;
+            for (int idx = tid; idx < k * W; idx += NT) {
+                const int r = idx / W, c = idx - r * W;
+                const int i = par[r];
+                xo[idx] = big[(size_t)i * W + c] * score[i];
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < W; c += NT) {  // readout: max / mean over the kept rows
+            const float *xo = xbuf + (size_t)(L.rowoff[1] + obase) * W + c;
+            float mx = -INFINITY, sum = 0.f;
+            int am = 0;
+            for (int r = 0; r < k; ++r) {
+                const float v = xo[(size_t)r * W];
+                if (v > mx) { mx = v; am = r; }
+                sum += v;
+            }
+            racc[gi * 2 * W + c] = mx;
+            racc[gi * 2 * W + W + c] = sum / (float)(k > 0 ? k : 1);
+            if (BWD) amaxs[(0 * G + gi) * W + c] = am;
+        }
+        if (nb > 1) filter_edges(E, e1s, e1d, 0, e2s + L.eoff[1], e2d + L.eoff[1], &ecnt[1]);
+        __syncthreads();
+    }
+
+    // ================================ blocks >= 1: rows of all `ng` graphs together ================================
+    for (int b = 1; b < nb; ++b) {
+        const int *sg = seg + b * (G + 1);
+        int *sgn = seg + (b + 1) * (G + 1);
+        const int nrows = sg[ng];
+        const int E = ecnt[b];
+        const float *X = xbuf + (size_t)L.rowoff[b] * W;
+        float *H = hbuf + (size_t)L.hoff[b] * W;
+        const int *es = e2s + L.eoff[b], *ed = e2d + L.eoff[b];
+        const int rbase = L.n_max + L.rowoff[b];
+        build_csr(nrows, E, es, ed, rowptr, cursor, csr);
+        if (net.blk[b].type == MDQ_BLOCK_SAGE) {
+            for (int idx = tid; idx < nrows * W; idx += NT) {
+                const int i = idx / W, f = idx - i * W;
+                const int s0 = rowptr[i], s1 = rowptr[i + 1];
+                float sum = 0.f;
+                for (int s = s0; s < s1; ++s) sum += X[(size_t)csr[s] * W + f];
+                const int cnt = s1 - s0;
+                cat2[(size_t)i * 2 * W + f] = sum / (float)(cnt > 0 ? cnt : 1);
+                cat2[(size_t)i * 2 * W + W + f] = X[idx];
+            }
+            __syncthreads();
+            dense_rows<false>(nrows, 2 * W, cat2, 2 * W, P + net.blk[b].w_off, P + net.blk[b].b_off, H, W, W, true);
+        } else {
+            for (int i = tid; i < nrows; i += NT) {
+                int deg = 1;
+                for (int s = rowptr[i]; s < rowptr[i + 1]; ++s) deg += (csr[s] != i);
+                dis[i] = __fdiv_rn(1.f, __fsqrt_rn((float)deg));
+            }
+            dense_rows<false>(nrows, W, X, W, P + net.blk[b].w_off, nullptr, cat2, W, W, false);
+            __syncthreads();
+            const float *bias = P + net.blk[b].b_off;
+            for (int idx = tid; idx < nrows * W; idx += NT) {
+                const int i = idx / W, c = idx - i * W;
+                const float di = dis[i];
+                float sum = 0.f;
+                for (int s = rowptr[i]; s < rowptr[i + 1]; ++s) {
+                    const int j = csr[s];
+                    if (j != i) sum += (dis[j] * di) * cat2[(size_t)j * W + c];
+                }
+                sum += (di * di) * cat2[idx];
+                sum += __ldg(bias + c);
+                H[idx] = fmaxf(sum, 0.f);
+            }
+        }
+        __syncthreads();
+        compute_scores(b, nrows, H, rbase);
+        if (tid == 0) {
+            int acc = 0;
+            sgn[0] = 0;
+            for (int gi = 0; gi < ng; ++gi) {
+                acc += topk_count_dev(net.ratio, sg[gi + 1] - sg[gi]);
+                sgn[gi + 1] = acc;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nrows; i += NT) {
+            int gi = 0;
+            while (gi + 1 < ng && i >= sg[gi + 1]) ++gi;
+            const int r0 = sg[gi], r1 = sg[gi + 1];
+            const int k = sgn[gi + 1] - sgn[gi];
+            const float si = score[rbase + i];
+            int r = 0;
+            for (int j = r0; j < r1; ++j) {
+                const float sj = score[rbase + j];
+                r += (sj > si) || (sj == si && j < i);
+            }
+            newid[rbase + i] = (r < k) ? (sgn[gi] + r) : -1;
+            if (r < k) parent[L.n_max + L.rowoff[b + 1] + sgn[gi] + r] = i;
+        }
+        __syncthreads();
+        {
+            const int nk = sgn[ng];
+            float *xo = xbuf + (size_t)L.rowoff[b + 1] * W;
+            const int *par = parent + L.n_max + L.rowoff[b + 1];
+            for (int idx = tid; idx < nk * W; idx += NT) {
+                const int r = idx / W, c = idx - r * W;
+                const int i = par[r];
+                xo[idx] = H[(size_t)i * W + c] * score[rbase + i];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < ng * W; idx += NT) {
+            const int gi = idx / W, c = idx - gi * W;
+            const int r0 = sgn[gi], r1 = sgn[gi + 1];
+            const float *xo = xbuf + (size_t)L.rowoff[b + 1] * W + c;
+            float mx = -INFINITY, sum = 0.f;
+            int am = 0;
+            for (int r = r0; r < r1; ++r) {
+                const float v = xo[(size_t)r * W];
+                if (v > mx) { mx = v; am = r - r0; }
+                sum += v;
+            }
+            const int k = r1 - r0;
+            racc[gi * 2 * W + c] += mx;
+            racc[gi * 2 * W + W + c] += sum / (float)(k > 0 ? k : 1);
+            if (BWD) amaxs[(b * G + gi) * W + c] = am;
+        }
+        if (b + 1 < nb) filter_edges(E, es, ed, rbase, e2s + L.eoff[b + 1], e2d + L.eoff[b + 1], &ecnt[b + 1]);
+        __syncthreads();
+    }
+
+    // ================================ MLP + softmax + argmax ================================
+    const int YM = L.ymax;
+    float *y1 = ybuf, *y2 = ybuf + G * YM, *y3 = ybuf + 2 * G * YM;
+    if (a.emb)
+        for (int idx = tid; idx < ng * 2 * W; idx += NT) a.emb[(size_t)g0 * 2 * W + idx] = racc[idx];
+    mlp_layer(ng, net.lin_in[0], net.lin_out[0], racc, 2 * W, P + net.lin_off[0], P + net.lin_boff[0], y1, YM, true, part);
+    mlp_layer(ng, net.lin_in[1], net.lin_out[1], y1, YM, P + net.lin_off[1], P + net.lin_boff[1], y2, YM, true, part);
+    mlp_layer(ng, net.lin_in[2], net.lin_out[2], y2, YM, P + net.lin_off[2], P + net.lin_boff[2], y3, YM, false, part);
+    const int A = net.out_dim;
+    for (int gi = warp; gi < ng; gi += NWARP) {
+        float *y = y3 + gi * YM;
+        if (net.softmax) {
+            float m = -INFINITY;
+            for (int c = lane; c < A; c += 32) m = fmaxf(m, y[c]);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+            float s = 0.f;
+            for (int c = lane; c < A; c += 32) {
+                const float e = expf(y[c] - m);
+                y[c] = e;
+                s += e;
+            }
+            s = warp_sum(s);
+            for (int c = lane; c < A; c += 32) y[c] = y[c] / s;
+        }
+        __syncwarp();
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < A; c += 32) {
+            const float v = y[c];
+            if (!BWD) a.out[(size_t)(g0 + gi) * A + c] = v;
+            if (v > bv) { bv = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (!BWD && a.amax_out && lane == 0) a.amax_out[g0 + gi] = bi;
+    }
+    if (!BWD) return;
+
+    // =====================================================================================
+    // backward (G == 1): rows of graph g0 only
+    // =====================================================================================
+    __syncthreads();
+    const int g = g0;
+    const WDesc &wd = a.wd;
+    float *ws = a.ws;
+    float *dx = smem + L.o_dx;
+    float *dp = smem + L.o_dp;
+    float *dcat = smem + L.o_dcat;
+    float *dr = smem + L.o_dr;          // [2W]
+    float *d1 = dr + 2 * W;             // [ymax] x3
+    float *d2 = d1 + YM;
+    float *d3 = d2 + YM;
+    float *tds = smem + L.o_tds;        // [gcap1][2] : ds*(1-s^2), unused
+
+    auto emit_row = [&](const WLayer &l, int r, const float *delta, const float *in, int in_n) {
+        float *dd = ws + l.d_off + ((size_t)g * l.rpg + r) * l.C;
+        for (int c = tid; c < l.C; c += NT) dd[c] = delta ? delta[c] : 0.f;
+        if (l.K > 0) {
+            float *ii = ws + l.i_off + ((size_t)g * l.rpg + r) * l.K;
+            for (int k = tid; k < l.K; k += NT) ii[k] = (in && k < in_n) ? in[k] : 0.f;
+        }
+    };
+
+    // ---- MLP backward ----
+    {
+        const float *go = a.gout + (size_t)g * A;
+        if (warp == 0) {
+            float dot = 0.f;
+            if (net.softmax) {
+                for (int c = lane; c < A; c += 32) dot = fmaf(__ldg(go + c), y3[c], dot);
+                dot = warp_sum(dot);
+            }
+            for (int c = lane; c < A; c += 32) {
+                const float gc = __ldg(go + c);
+                d3[c] = net.softmax ? y3[c] * (gc - dot) : gc;
+            }
+        }
+        __syncthreads();
+        emit_row(wd.l[2 * nb + 2], 0, d3, y2, net.lin_in[2]);
+        matvec_t(net.lin_in[2], net.lin_out[2], d3, P + net.lin_off[2], d2, y2);
+        __syncthreads();
+        emit_row(wd.l[2 * nb + 1], 0, d2, y1, net.lin_in[1]);
+        matvec_t(net.lin_in[1], net.lin_out[1], d2, P + net.lin_off[1], d1, y1);
+        __syncthreads();
+        emit_row(wd.l[2 * nb + 0], 0, d1, racc, net.lin_in[0]);
+        matvec_t(net.lin_in[0], net.lin_out[0], d1, P + net.lin_off[0], dr, nullptr);
+        __syncthreads();
+    }
+
+    // ---- conv blocks, last to first ----
+    for (int b = nb - 1; b >= 0; --b) {
+        const int n_b = (b == 0) ? (a.nptr[g + 1] - a.nptr[g]) : seg[b * (G + 1) + 1];
+        const int k = seg[(b + 1) * (G + 1) + 1];  // kept rows (G == 1)
+        const float *H = (b == 0) ? big : hbuf + (size_t)L.hoff[b] * W;
+        const int rbase = (b == 0) ? 0 : L.n_max + L.rowoff[b];
+        const int *par = parent + L.n_max + L.rowoff[b + 1];
+        const float *dxn = dx + (size_t)L.rowoff[b + 1] * W;  // valid when b+1 < nb
+        const int *am = amaxs + (b * G) * W;
+        const WLayer &lw = wd.l[b];
+        const bool sage = net.blk[b].type == MDQ_BLOCK_SAGE;
+        // dXn -> dp (temporarily holds dXn), ds per kept row
+        for (int idx = tid; idx < k * W; idx += NT) {
+            const int r = idx / W, c = idx - r * W;
+            float v = (b + 1 < nb) ? dxn[idx] : 0.f;
+            v += dr[W + c] / (float)k;
+            if (am[c] == r) v += dr[c];
+            dp[idx] = v;
+        }
+        __syncthreads();
+        {
+            float pw[8], wnorm;
+            pool_weights(b, pw, wnorm);
+            for (int r = warp; r < k; r += NWARP) {
+                const int i = par[r];
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j;
+                    if (c < W) acc = fmaf(dp[r * W + c], H[(size_t)i * W + c], acc);
+                }
+                acc = warp_sum(acc);
+                const float s = score[rbase + i];
+                if (lane == 0) tds[r] = acc * (1.f - s * s);
+            }
+            __syncthreads();
+            // pool weight gradient (per-graph partial, sequential over kept rows) and dP
+            const float *wp = P + net.blk[b].pool_off;
+            float *dpool = ws + wd.l[nb + b].d_off + (size_t)g * W;
+            for (int c = tid; c < W; c += NT) {
+                const float wc = __ldg(wp + c);
+                float accw = 0.f;
+                for (int r = 0; r < k; ++r) {
+                    const int i = par[r];
+                    accw += tds[r] * (H[(size_t)i * W + c] / wnorm - zval[rbase + i] * wc / (wnorm * wnorm));
+                }
+                dpool[c] = accw;
+            }
+            for (int idx = tid; idx < k * W; idx += NT) {
+                const int r = idx / W, c = idx - r * W;
+                const int i = par[r];
+                const float h = H[(size_t)i * W + c];
+                const float dh = dp[idx] * score[rbase + i] + tds[r] * __ldg(wp + c) / wnorm;
+                dp[idx] = (h > 0.f) ? dh : 0.f;
+            }
+        }
+        __syncthreads();
+        if (b == 0) {
+            for (int r = 0; r < lw.rpg; ++r)
+                emit_row(lw, r, r < k ? dp + r * W : nullptr, r < k ? cat1 + par[r] * KC1 : nullptr, 2 * F);
+            break;
+        }
+        const float *X = xbuf + (size_t)L.rowoff[b] * W;
+        const int E = ecnt[b];
+        build_csr(n_b, E, e2s + L.eoff[b], e2d + L.eoff[b], rowptr, cursor, csr);
+        float *dxb = dx + (size_t)L.rowoff[b] * W;
+        if (sage) {
+            // inputs of the kept rows: [mean agg | x] recomputed into cat2 rows 0..k-1
+            for (int idx = tid; idx < k * W; idx += NT) {
+                const int r = idx / W, f = idx - r * W;
+                const int i = par[r];
+                const int s0 = rowptr[i], s1 = rowptr[i + 1];
+                float sum = 0.f;
+                for (int s = s0; s < s1; ++s) sum += X[(size_t)csr[s] * W + f];
+                const int cnt = s1 - s0;
+                cat2[(size_t)r * 2 * W + f] = sum / (float)(cnt > 0 ? cnt : 1);
+                cat2[(size_t)r * 2 * W + W + f] = X[(size_t)i * W + f];
+            }
+            __syncthreads();
+            for (int r = 0; r < lw.rpg; ++r)
+                emit_row(lw, r, r < k ? dp + r * W : nullptr, r < k ? cat2 + (size_t)r * 2 * W : nullptr, 2 * W);
+            // dcat[r][kk] = sum_c dP[r][c] * WT[kk][c]
+            const float *WT = P + net.blk[b].w_off;
+            for (int t = warp; t < k * 2 * W; t += NWARP) {
+                const int r = t / (2 * W), kk = t - r * 2 * W;
+                float acc = 0.f;
+                for (int c = lane; c < W; c += 32) acc = fmaf(dp[r * W + c], __ldg(WT + (size_t)kk * W + c), acc);
+                acc = warp_sum(acc);
+                if (lane == 0) dcat[t] = acc;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < n_b * W; idx += NT) {
+                const int j = idx / W, f = idx - j * W;
+                float acc = 0.f;
+                for (int r = 0; r < k; ++r) {
+                    const int i = par[r];
+                    if (i == j) acc += dcat[(size_t)r * 2 * W + W + f];
+                    const int s0 = rowptr[i], s1 = rowptr[i + 1];
+                    const float cnt = (float)(s1 - s0 > 0 ? s1 - s0 : 1);
+                    for (int s = s0; s < s1; ++s)
+                        if (csr[s] == j) acc += dcat[(size_t)r * 2 * W + f] / cnt;
+                }
+                dxb[idx] = acc;
+            }
+        } else {
+            for (int i = tid; i < n_b; i += NT) {
+                int deg = 1;
+                for (int s = rowptr[i]; s < rowptr[i + 1]; ++s) deg += (csr[s] != i);
+                dis[i] = __fdiv_rn(1.f, __fsqrt_rn((float)deg));
+            }
+            // GCN bias gradient: sum of dP over the kept rows
+            {
+                float *db = ws + wd.l[2 * nb + 3 + b].d_off + (size_t)g * W;
+                for (int c = tid; c < W; c += NT) {
+                    float acc = 0.f;
+                    for (int r = 0; r < k; ++r) acc += dp[r * W + c];
+                    db[c] = acc;
+                }
+            }
+            __syncthreads();
+            // dXW[j][c] into dcat [n_b][W]
+            for (int idx = tid; idx < n_b * W; idx += NT) {
+                const int j = idx / W, c = idx - j * W;
+                float acc = 0.f;
+                for (int r = 0; r < k; ++r) {
+                    const int i = par[r];
+                    const float di = dis[i];
+                    for (int s = rowptr[i]; s < rowptr[i + 1]; ++s)
+                        if (csr[s] == j && j != i) acc += (dis[j] * di) * dp[r * W + c];
+                    if (i == j) acc += (di * di) * dp[r * W + c];
+                }
+                dcat[idx] = acc;
+            }
+            __syncthreads();
+            for (int r = 0; r < lw.rpg; ++r)
+                emit_row(lw, r, r < n_b ? dcat + (size_t)r * W : nullptr, r < n_b ? X + (size_t)r * W : nullptr, W);
+            const float *WT = P + net.blk[b].w_off;
+            for (int t = warp; t < n_b * W; t += NWARP) {
+                const int j = t / W, kk = t - j * W;
+                float acc = 0.f;
+                for (int c = lane; c < W; c += 32) acc = fmaf(dcat[(size_t)j * W + c], __ldg(WT + (size_t)kk * W + c), acc);
+                acc = warp_sum(acc);
+                if (lane == 0) dxb[t] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: partial[s][k][c] = sum_{rows in chunk s} in[row][k] * delta[row][c]   (k == K -> bias)
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 128;  // rows per chunk
+constexpr int WG_KG = 8;      // k values per thread
+
+// layer li: S chunks of WG_ROWS rows, nkg groups of WG_KG k-values; partial offset = sum over earlier layers
+__device__ __forceinline__ void wg_layer_geom(const WDesc &wd, int B, int li, int &S, int &nkg, int &poff)
+{
+    int off = 0;
+    for (int i = 0; i < li; ++i) {
+        const int rows = B * wd.l[i].rpg;
+        if (rows == 0) continue;
+        off += ((rows + WG_ROWS - 1) / WG_ROWS) * ((wd.l[i].K + 1 + WG_KG - 1) / WG_KG) * WG_KG * wd.l[i].C;
+    }
+    const int rows = B * wd.l[li].rpg;
+    S = (rows + WG_ROWS - 1) / WG_ROWS;
+    nkg = (wd.l[li].K + 1 + WG_KG - 1) / WG_KG;
+    poff = off;
+}
+
+__global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int B, const float *__restrict__ ws,
+                                                            float *__restrict__ partial)
+{
+    const int li = blockIdx.y;
+    const WLayer l = wd.l[li];
+    if (l.rpg == 0) return;
+    int S, nkg, poff;
+    wg_layer_geom(wd, B, li, S, nkg, poff);
+    const int KB = l.K + 1;  // last "k" is the bias column (input == 1)
+    for (int t = blockIdx.x; t < S * nkg; t += gridDim.x) {
+        const int kg = t / S, chunk = t - kg * S;
+        const int rows = B * l.rpg;
+        const int r0 = chunk * WG_ROWS, r1 = min(rows, r0 + WG_ROWS);
+        const int k0 = kg * WG_KG;
+        float *po = partial + poff + (size_t)t * WG_KG * l.C;
+        for (int c = threadIdx.x; c < l.C; c += blockDim.x) {
+            float acc[WG_KG];
+#pragma unroll
+            for (int j = 0; j < WG_KG; ++j) acc[j] = 0.f;
+            const float *dl = ws + l.d_off + c;
+            const float *in = ws + l.i_off;
+            for (int r = r0; r < r1; ++r) {
+                const float d = __ldg(dl + (size_t)r * l.C);
+#pragma unroll
+                for (int j = 0; j < WG_KG; ++j) {
+                    const int k = k0 + j;
+                    const float xv = (k < l.K) ? __ldg(in + (size_t)r * l.K + k) : (k == l.K ? 1.f : 0.f);
+                    acc[j] = fmaf(xv, d, acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < WG_KG; ++j)
+                if (k0 + j < KB) po[(size_t)j * l.C + c] = acc[j];
+        }
+    }
+}
+
+// grad[w_off + k*C + c] = sum_s partial[kg][s][kj][c] in chunk order; k == K is the bias / pool-weight row
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WDesc wd, int B, const float *__restrict__ partial,
+                                                           float *__restrict__ grad)
+{
+    const int li = blockIdx.y;
+    const WLayer l = wd.l[li];
+    if (l.rpg == 0) return;
+    int S, nkg, poff;
+    wg_layer_geom(wd, B, li, S, nkg, poff);
+    const int KB = l.K + 1;
+    const float *pl = partial + poff;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < KB * l.C; idx += gridDim.x * blockDim.x) {
+        const int k = idx / l.C, c = idx - k * l.C;
+        const int kg = k / WG_KG, kj = k - kg * WG_KG;
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += pl[((size_t)(kg * S + s) * WG_KG + kj) * l.C + c];
+        if (k < l.K) {
+            if (l.w_off >= 0) grad[l.w_off + (size_t)k * l.C + c] = acc;
+        } else if (l.b_off >= 0) {
+            grad[l.b_off + c] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Huber replay loss + Adam
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) huber_kernel(const float *__restrict__ q1, const float *__restrict__ q2,
+                                                    const int *__restrict__ action, const float *__restrict__ reward,
+                                                    const int *__restrict__ next_slot, int B, int n_next, int A,
+                                                    float gamma, int select, float *loss, float *gq1, float *gq2)
+{
+    __shared__ float red[256];
+    const int tid = threadIdx.x;
+    // zero the gradient buffer this call owns
+    if (select) { for (int i = tid; i < B * A; i += 256) gq1[i] = 0.f; }
+    else { for (int i = tid; i < n_next * A; i += 256) gq2[i] = 0.f; }
+    __syncthreads();
+    float lsum = 0.f;
+    for (int b = tid; b < B; b += 256) {
+        const int act = action[b];
+        const float pred = q1[(size_t)b * A + act];
+        const int slot = next_slot[b];
+        float nsv = 0.f;
+        int am = 0;
+        if (slot >= 0) {
+            const float *q = q2 + (size_t)slot * A;
+            float m = q[0];
+            for (int c = 1; c < A; ++c)
+                if (q[c] > m) { m = q[c]; am = c; }
+            nsv = m;
+        }
+        const float target = nsv * gamma + reward[b];
+        const float d = pred - target;
+        const float ad = fabsf(d);
+        lsum += (ad < 1.f) ? 0.5f * d * d : (ad - 0.5f);
+        const float gd = ((ad < 1.f) ? d : (d > 0.f ? 1.f : -1.f)) / (float)B;
+        if (select) gq1[(size_t)b * A + act] = gd;
+        else if (slot >= 0) gq2[(size_t)slot * A + am] = -gd * gamma;
+    }
+    red[tid] = lsum;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) *loss = red[0] / (float)B;
+}
+
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                            float gscale, float step_size, float bc2_sqrt)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        const float pi = p[i];
+        gi = fmaf(wd, pi, gi);
+        const float m0 = m[i];
+        const float mi = fmaf(gi - m0, 1.f - b1, m0);  // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
+int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, void (*kern)(const QArgs))
+{
+    int rc = build_layout(*net, max_n, max_e, G, bwd, L);
+    if (rc != MDQ_OK) { mdq::set_error("qnet: unsupported network/size (rc=%d)", rc); return rc; }
+    const size_t bytes = (size_t)L.total * 4;
+    if (bytes > 227 * 1024) {
+        mdq::set_error("qnet: graphs of %d nodes / %d edges need %zu B of shared memory (> 227 KB) with %d graph(s)/CTA",
+                       max_n, max_e, bytes, G);
+        return MDQ_ESMEM;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { mdq::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
+    return MDQ_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int64_t mdq_qnet_smem_bytes(const mdq_net_t *net, int max_n, int max_e, int gpc, int backward)
+{
+    QLay L;
+    if (build_layout(*net, max_n, max_e, gpc, backward, L) != MDQ_OK) return -1;
+    return (int64_t)L.total * 4;
+}
+
+int mdq_qnet_pick_gpc(const mdq_net_t *net, int n_graphs, int max_n, int max_e)
+{
+    // smallest graphs-per-CTA that brings the grid to one wave of 148 CTAs, limited by shared memory
+    int best = 1;
+    for (int G = 1; G <= 4; ++G) {
+        QLay L;
+        if (build_layout(*net, max_n, max_e, G, 0, L) != MDQ_OK) break;
+        if ((size_t)L.total * 4 > 227 * 1024) break;
+        best = G;
+        if ((n_graphs + G - 1) / G <= 148) break;
+    }
+    return best;
+}
+
+int mdq_qnet_forward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                     const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                     int max_n, int max_e, float *out, float *embedding, int32_t *argmax, void *stream)
+{
+    if (!net || !params || !x || !node_ptr || !edge_ptr || !out || n_graphs < 1) {
+        mdq::set_error("mdq_qnet_forward: null argument or empty batch");
+        return MDQ_EINVAL;
+    }
+    const int G = mdq_qnet_pick_gpc(net, n_graphs, max_n, max_e);
+    QArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = setup_launch(net, max_n, max_e, G, 0, a.L, qnet_kernel<false>);
+    if (rc != MDQ_OK) return rc;
+    a.net = *net;
+    a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
+    a.B = n_graphs; a.out = out; a.emb = embedding; a.amax_out = argmax;
+    const int grid = (n_graphs + G - 1) / G;
+    qnet_kernel<false><<<grid, NT, (size_t)a.L.total * 4, (cudaStream_t)stream>>>(a);
+    return mdq::check_launch("qnet_kernel<fwd>");
+}
+
+int64_t mdq_qnet_bwd_workspace_floats(const mdq_net_t *net, int n_graphs, int max_n)
+{
+    WDesc wd;
+    if (build_wdesc(*net, n_graphs, max_n, wd) != MDQ_OK) return -1;
+    // rows workspace + split-K partials + task tables (ints stored in the same buffer)
+    int64_t partial = 0, tasks = 0;
+    for (int i = 0; i < wd.nl; ++i) {
+        const WLayer &l = wd.l[i];
+        if (l.rpg == 0) continue;
+        const int rows = n_graphs * l.rpg;
+        const int S = (rows + WG_ROWS - 1) / WG_ROWS;
+        const int nkg = (l.K + 1 + WG_KG - 1) / WG_KG;
+        partial += (int64_t)S * nkg * WG_KG * l.C;
+        tasks += (int64_t)S * nkg;
+    }
+    (void)tasks;
+    return (int64_t)wd.total + partial + 64;
+}
+
+int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                      const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                      int max_n, int max_e, const float *grad_out, float *grad, float *workspace, void *stream)
+{
+    if (!net || !params || !x || !grad_out || !grad || !workspace || n_graphs < 1) {
+        mdq::set_error("mdq_qnet_backward: null argument or empty batch");
+        return MDQ_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    QArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = setup_launch(net, max_n, max_e, 1, 1, a.L, qnet_kernel<true>);
+    if (rc != MDQ_OK) return rc;
+    build_wdesc(*net, n_graphs, max_n, a.wd);
+    a.net = *net;
+    a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
+    a.B = n_graphs; a.gout = grad_out; a.ws = workspace;
+
+    const WDesc &wd = a.wd;
+    int max_tasks = 1;
+    for (int i = 0; i < wd.nl; ++i) {
+        const WLayer &l = wd.l[i];
+        if (l.rpg == 0) continue;
+        const int S = (n_graphs * l.rpg + WG_ROWS - 1) / WG_ROWS;
+        const int nkg = (l.K + 1 + WG_KG - 1) / WG_KG;
+        if (S * nkg > max_tasks) max_tasks = S * nkg;
+    }
+    float *d_partial = workspace + wd.total;
+    cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net->n_params * sizeof(float), st);
+    if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
+
+    qnet_kernel<true><<<n_graphs, NT, (size_t)a.L.total * 4, st>>>(a);
+    rc = mdq::check_launch("qnet_kernel<bwd>");
+    if (rc != MDQ_OK) return rc;
+    dim3 pg(max_tasks, wd.nl);
+    wgrad_partial_kernel<<<pg, 256, 0, st>>>(a.wd, n_graphs, workspace, d_partial);
+    rc = mdq::check_launch("wgrad_partial_kernel");
+    if (rc != MDQ_OK) return rc;
+    dim3 rg(16, wd.nl);
+    wgrad_reduce_kernel<<<rg, 256, 0, st>>>(a.wd, n_graphs, d_partial, grad);
+    return mdq::check_launch("wgrad_reduce_kernel");
+}
+
+int mdq_huber_replay(const float *q1, const float *q2, const int32_t *action, const float *reward,
+                     const int32_t *next_slot, int batch, int n_next, int out_dim, float gamma, int select,
+                     float *loss, float *grad_q1, float *grad_q2, void *stream)
+{
+    if (!q1 || !action || !reward || !next_slot || !loss || batch < 1 || (select ? !grad_q1 : !grad_q2)) {
+        mdq::set_error("mdq_huber_replay: null argument");
+        return MDQ_EINVAL;
+    }
+    huber_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(q1, q2, action, reward, next_slot, batch, n_next, out_dim, gamma,
+                                                      select, loss, grad_q1, grad_q2);
+    return mdq::check_launch("huber_kernel");
+}
+
+int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step, void *stream)
+{
+    if (!params || !grad || !exp_avg || !exp_avg_sq || n < 1 || step < 1) {
+        mdq::set_error("mdq_adam_step: bad argument");
+        return MDQ_EINVAL;
+    }
+    const double bc1d = 1.0 - pow((double)beta1, (double)step);
+    const double bc2d = 1.0 - pow((double)beta2, (double)step);
+    const int threads = 256;
+    int blocks = (int)((n + threads - 1) / threads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                              weight_decay, grad_scale, (float)((double)lr / bc1d), (float)sqrt(bc2d));
+    return mdq::check_launch("adam_kernel");
+}
+
+}  // extern "C"

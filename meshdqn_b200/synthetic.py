@@ -1,0 +1,143 @@
+"""Seeded synthetic inputs: velocity/pressure snapshots and refined airfoil-channel meshes.
+
+The reference's fields come from a 5000-step FEniCS Navier-Stokes solve
+(/root/reference/Env2DAirfoil.py:111-125, flow_solver.py:362-396) that stays
+outside this repo; no solution ships with the reference.  Tests and bench
+therefore use analytic, smooth, phase-shifted P2/P1 nodal fields with the
+channel parabola of flow_solver.py:33-44 as the base flow, and
+`synthetic_airfoil_mesh` builds the ~250k / ~1M-triangle meshes BASELINE.json
+names (vertex order as in the shipped fixtures: corners, airfoil ring in curve
+order, outer wall points, interior).
+Input generation only -- not part of the timed hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def field_values(pts, T=5, seed=0):
+    """Analytic snapshots at points [n,2] -> (u [T,n,2], p [T,n]) float64."""
+    rng = np.random.RandomState(seed)
+    ph0 = rng.uniform(0, 2 * np.pi)
+    amp = rng.uniform(0.05, 0.15, size=3)
+    x, y = pts[:, 0], pts[:, 1]
+    bot, top = -0.5, 0.5
+    H = top - bot
+    par = -4 * 1.5 * (y - bot) * (y - top) / H / H
+    cx, cy = 0.5, 0.0
+    g = 1.0 - np.exp(-(((x - cx) / 0.45) ** 2 + ((y - cy) / 0.12) ** 2))
+    u = np.empty((T, len(pts), 2))
+    p = np.empty((T, len(pts)))
+    for t in range(T):
+        ph = ph0 + 0.4 * t
+        u[t, :, 0] = par * g * (1.0 + amp[0] * np.sin(2 * np.pi * (x - 0.2 * t) + ph))
+        u[t, :, 1] = amp[1] * np.sin(np.pi * x + ph) * np.cos(np.pi * y) * g * 2.0
+        p[t] = 0.3 * (3.0 - x) + 0.5 * np.exp(-((x - cx) ** 2 + (y - cy) ** 2) / 0.1) * np.cos(ph) \
+            + amp[2] * np.sin(2 * np.pi * y + ph)
+    return u, p
+
+
+def synthetic_fields(coords, edges, T=5, seed=0):
+    """Nodal P2 vector / P1 scalar coefficients on a mesh.
+
+    Returns ``U [T, V+E, 2]`` (vertex dofs then edge-midpoint dofs) and ``P [T, V]``.
+    """
+    mid = 0.5 * coords[edges[:, 0]] + 0.5 * coords[edges[:, 1]]
+    pts = np.concatenate([coords, mid], axis=0)
+    u, p = field_values(pts, T, seed)
+    return np.ascontiguousarray(u), np.ascontiguousarray(p[:, : len(coords)])
+
+
+def _naca_ring(n, chord=1.0, t=0.12, m=0.02, pc=0.4, x0=0.0, y0=0.0):
+    """Closed NACA 4-digit contour, n points in curve order (upper TE->LE, lower LE->TE)."""
+    nu = n // 2 + 1
+    beta = np.linspace(0.0, np.pi, nu)
+    xc = 0.5 * (1 + np.cos(beta))  # 1 -> 0
+    def thick(xx):
+        return 5 * t * (0.2969 * np.sqrt(xx) - 0.1260 * xx - 0.3516 * xx ** 2 + 0.2843 * xx ** 3 - 0.1036 * xx ** 4)
+    def camber(xx):
+        return np.where(xx < pc, m / pc ** 2 * (2 * pc * xx - xx ** 2), m / (1 - pc) ** 2 * ((1 - 2 * pc) + 2 * pc * xx - xx ** 2))
+    up = np.stack([xc, camber(xc) + thick(xc)], 1)
+    xl = xc[::-1][1:-1] if n % 2 == 0 else xc[::-1][1:]
+    xl = xl[: n - nu]
+    lo = np.stack([xl, camber(xl) - thick(xl)], 1)
+    ring = np.concatenate([up, lo], 0)[:n]
+    ring[:, 0] = ring[:, 0] * chord + x0
+    ring[:, 1] = ring[:, 1] * chord + y0
+    return ring
+
+
+def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None):
+    """Graded Delaunay mesh of the channel [-0.5,3]x[-0.5,0.5] minus a NACA-style hole.
+
+    Cells whose three vertices are all boundary points are dropped, the same rule the
+    reference applies after re-triangulating (Env2DAirfoil.py:496).  Returns
+    ``(coords f64 [V,2], cells i32 [C,3], n_ring)``.
+    """
+    from scipy.spatial import Delaunay
+
+    rng = np.random.RandomState(seed)
+    nv_target = max(64, n_triangles // 2)
+    n_af = n_airfoil or int(max(40, 6.0 * np.sqrt(nv_target)))
+    ring = _naca_ring(n_af, chord=1.0, x0=0.0, y0=0.0)
+    # outer boundary points
+    h_wall = max(3.5 / (2.0 * np.sqrt(nv_target)), 1e-4)
+    nx = int(np.ceil(3.5 / h_wall))
+    ny = int(np.ceil(1.0 / h_wall))
+    xs = np.linspace(-0.5, 3.0, nx + 1)[1:-1]
+    ys = np.linspace(-0.5, 0.5, ny + 1)[1:-1]
+    corners = np.array([[-0.5, -0.5], [3.0, -0.5], [3.0, 0.5], [-0.5, 0.5]])
+    walls = np.concatenate([
+        np.stack([xs, np.full_like(xs, -0.5)], 1), np.stack([xs, np.full_like(xs, 0.5)], 1),
+        np.stack([np.full_like(ys, -0.5), ys], 1), np.stack([np.full_like(ys, 3.0), ys], 1)])
+    nb = 4 + len(ring) + len(walls)
+    n_int = max(16, nv_target - nb)
+    # graded interior cloud: rejection-sample density ~ 1/h^2, h = h0 + a*dist(chord)
+    pts = []
+    got = 0
+    h0, a = 0.02, 1.0
+    # polygon test helpers (ring is a simple polygon)
+    def inside_ring(q):
+        xq, yq = q[:, 0], q[:, 1]
+        ins = np.zeros(len(q), dtype=bool)
+        ax, ay = ring[:, 0], ring[:, 1]
+        bx, by = np.roll(ax, -1), np.roll(ay, -1)
+        for k in range(len(ring)):
+            cond = (ay[k] > yq) != (by[k] > yq)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                xi = ax[k] + (yq - ay[k]) * (bx[k] - ax[k]) / (by[k] - ay[k])
+            ins ^= cond & (xq < xi)
+        return ins
+    while got < n_int:
+        m = int((n_int - got) * 3) + 1024
+        q = np.stack([rng.uniform(-0.5, 3.0, m), rng.uniform(-0.5, 0.5, m)], 1)
+        dx = np.clip(q[:, 0], 0.0, 1.0) - q[:, 0]
+        d = np.sqrt(dx ** 2 + q[:, 1] ** 2)
+        h = h0 + a * d
+        acc = rng.uniform(0, 1, m) < (h0 / h) ** 2
+        q = q[acc]
+        # keep points clear of the hole and of the boundaries
+        near = (q[:, 0] > -0.05) & (q[:, 0] < 1.05) & (np.abs(q[:, 1]) < 0.2)
+        bad = np.zeros(len(q), dtype=bool)
+        if near.any():
+            qn = q[near]
+            insn = inside_ring(qn)
+            # distance to ring vertices as a cheap clearance test
+            step = max(1, len(ring) // 256)
+            rr = ring[::step]
+            dmin = np.sqrt(((qn[:, None, :] - rr[None, :, :]) ** 2).sum(-1)).min(1) if len(qn) < 200000 else \
+                np.full(len(qn), 1.0)
+            bad[np.nonzero(near)[0]] = insn | (dmin < 0.5 * (2.2 / n_af))
+        bad |= (q[:, 0] < -0.5 + 0.5 * h_wall) | (q[:, 0] > 3.0 - 0.5 * h_wall) | (np.abs(q[:, 1]) > 0.5 - 0.5 * h_wall)
+        q = q[~bad]
+        pts.append(q)
+        got += len(q)
+    interior = np.concatenate(pts, 0)[:n_int]
+    coords = np.concatenate([corners, ring, walls, interior], 0)
+    tri = Delaunay(coords)
+    cells = tri.simplices
+    is_b = np.zeros(len(coords), dtype=bool)
+    is_b[:nb] = True
+    cells = cells[is_b[cells].sum(1) != 3]
+    cells = np.sort(cells, axis=1).astype(np.int32)
+    return np.ascontiguousarray(coords), np.ascontiguousarray(cells), len(ring)
