@@ -32,7 +32,7 @@ struct QLay {
     int xrows, e2cap, nrow_all, ymax;
     int o_w1, o_cat1, o_big, o_cat2, o_xbuf, o_hbuf, o_e1s, o_e1d, o_csr, o_e2s, o_e2d;
     int o_rowptr, o_cursor, o_score, o_z, o_newid, o_parent, o_dis, o_seg, o_ecnt, o_racc, o_y, o_part;
-    int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds;
+    int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds, o_h1k;
     int total;  // 4-byte words
 };
 
@@ -108,9 +108,20 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     auto take = [&](int words) { int at = o; o += mdq::pad4(words); return at; };
     L.o_w1 = take((L.KC1 + 1) * W);
     L.o_cat1 = take(max_n * L.KC1);
-    const int big_fwd = max_n * W > gcap1 * 2 * W ? max_n * W : gcap1 * 2 * W;
-    L.o_big = take(bwd ? max_n * W : big_fwd);
-    L.o_cat2 = bwd ? take(gcap1 * 2 * W) : L.o_big;
+    // `big` holds block 0's hidden rows H1 [n][W]; once block 0 is done the same words hold block >= 1
+    // scratch: cat2 (forward and backward) and, in the backward kernel, dx / dp / dcat as well.
+    const int dcat_a = G * L.ncap[nb > 1 ? 2 : 1] * 2 * W, dcat_c = gcap1 * W;
+    const int dcat_words = dcat_a > dcat_c ? dcat_a : dcat_c;
+    int alias_words = mdq::pad4(gcap1 * 2 * W);
+    if (bwd) alias_words += mdq::pad4(L.xrows * W) + mdq::pad4(gcap1 * W) + mdq::pad4(dcat_words);
+    L.o_big = take(max_n * W > alias_words ? max_n * W : alias_words);
+    L.o_cat2 = L.o_big;
+    if (bwd) {
+        L.o_dx = L.o_cat2 + mdq::pad4(gcap1 * 2 * W);
+        L.o_dp = L.o_dx + mdq::pad4(L.xrows * W);
+        L.o_dcat = L.o_dp + mdq::pad4(gcap1 * W);
+        L.o_h1k = take(gcap1 * W);  // block 0's kept hidden rows, saved before `big` is reused
+    }
     L.o_xbuf = take(L.xrows * W);
     L.o_hbuf = take((bwd ? L.xrows : gcap1) * W);
     L.o_e1s = take(L.e_max);
@@ -132,10 +143,6 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     L.o_y = take(G * 3 * L.ymax);
     L.o_part = take(MLP_SPLIT * G * L.ymax);
     if (bwd) {
-        L.o_dx = take(L.xrows * W);
-        L.o_dp = take(gcap1 * W);
-        const int a = G * L.ncap[nb > 1 ? 2 : 1] * 2 * W, c = gcap1 * W;
-        L.o_dcat = take(a > c ? a : c);
         L.o_dr = take(2 * W + 3 * L.ymax);
         L.o_amax = take(nb * G * W);
         L.o_tds = take(gcap1 * 2);
@@ -482,7 +489,9 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
             for (int idx = tid; idx < k * W; idx += NT) {
                 const int r = idx / W, c = idx - r * W;
                 const int i = par[r];
-                xo[idx] = big[(size_t)i * W + c] * score[i];
+                const float h = big[(size_t)i * W + c];
+                xo[idx] = h * score[i];
+                if (BWD) (smem + L.o_h1k)[(size_t)(obase + r) * W + c] = h;
             }
         }
         __syncthreads();
@@ -703,7 +712,9 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
     for (int b = nb - 1; b >= 0; --b) {
         const int n_b = (b == 0) ? (a.nptr[g + 1] - a.nptr[g]) : seg[b * (G + 1) + 1];
         const int k = seg[(b + 1) * (G + 1) + 1];  // kept rows (G == 1)
-        const float *H = (b == 0) ? big : hbuf + (size_t)L.hoff[b] * W;
+        // hidden rows of block b: block 0 keeps only its kept rows (compact, row r); blocks >= 1 keep all rows
+        const float *H = (b == 0) ? smem + L.o_h1k : hbuf + (size_t)L.hoff[b] * W;
+        const bool compactH = (b == 0);
         const int rbase = (b == 0) ? 0 : L.n_max + L.rowoff[b];
         const int *par = parent + L.n_max + L.rowoff[b + 1];
         const float *dxn = dx + (size_t)L.rowoff[b + 1] * W;  // valid when b+1 < nb
@@ -728,7 +739,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = lane + 32 * j;
-                    if (c < W) acc = fmaf(dp[r * W + c], H[(size_t)i * W + c], acc);
+                    if (c < W) acc = fmaf(dp[r * W + c], H[(size_t)(compactH ? r : i) * W + c], acc);
                 }
                 acc = warp_sum(acc);
                 const float s = score[rbase + i];
@@ -743,14 +754,14 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
                 float accw = 0.f;
                 for (int r = 0; r < k; ++r) {
                     const int i = par[r];
-                    accw += tds[r] * (H[(size_t)i * W + c] / wnorm - zval[rbase + i] * wc / (wnorm * wnorm));
+                    accw += tds[r] * (H[(size_t)(compactH ? r : i) * W + c] / wnorm - zval[rbase + i] * wc / (wnorm * wnorm));
                 }
                 dpool[c] = accw;
             }
             for (int idx = tid; idx < k * W; idx += NT) {
                 const int r = idx / W, c = idx - r * W;
                 const int i = par[r];
-                const float h = H[(size_t)i * W + c];
+                const float h = H[(size_t)(compactH ? r : i) * W + c];
                 const float dh = dp[idx] * score[rbase + i] + tds[r] * __ldg(wp + c) / wnorm;
                 dp[idx] = (h > 0.f) ? dh : 0.f;
             }

@@ -1,0 +1,175 @@
+"""Replay-minibatch training step on device (data parallel over NCCL).
+
+Restates the math of ``DataWorker._get_data`` / ``compute_gradients`` and the parameter
+server's Adam step (/root/reference/airfoil_dqn.py:172-176, 240-310):
+
+    pred   = Q1(s)[a]                                      (:264)
+    target = r + gamma * max_a Q2(s')   (0 when s' is terminal)   (:267-281)
+    loss   = HuberLoss(delta=1, mean)(pred, target)        (:303-304)
+    backward through the *selected* net only               (:258-262, 272-276)
+    Adam(lr, weight_decay) + MultiStepLR([500k, 1M, 1.5M], 0.1)   (:172-176)
+
+The reference routes this through Ray actors (replay actor -> worker -> parameter server); its
+apply_gradients steps the optimizer before the gradients are set and re-creates the optimizer on
+every call, losing Adam's moments (:188-199).  Those are defects, not semantics (SURVEY.md App. B,
+"do not replicate"): here each net keeps one Adam state and the step is
+forward(Q1) -> forward(Q2) -> Huber -> backward(selected) -> [all-reduce] -> Adam, 7 launches.
+
+Multi-GPU: graphs are independent, so each rank takes its own B transitions; the only exchange is
+ONE all-reduce (sum) of the flat fp32 gradient (the first ``n_used`` floats of the flat buffer,
+~0.5 MB) over NCCL/NVLink; the mean over ranks is folded into the Adam kernel (grad_scale).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .airfoilgcnn import graph_ptrs
+
+
+class ReplayBatch:
+    """A collated minibatch resident on one device.
+
+    states / next_states: ``Batch`` objects; ``next_slot`` i32 [B] = row of ``next_states`` holding
+    transition b's next state, -1 if terminal; ``actions`` i32 [B]; ``rewards`` f32 [B].
+    """
+
+    def __init__(self, states, actions, next_states, next_slot, rewards):
+        self.states, self.actions, self.next_states, self.next_slot, self.rewards = \
+            states, actions, next_states, next_slot, rewards
+
+    @classmethod
+    def from_transitions(cls, transitions):
+        """transitions: iterable of (state Data, action int, next_state Data | None, reward float)
+        -- the reference's ``Transition`` tuples (airfoil_dqn.py:46-47)."""
+        from .data import Batch
+        states, actions, nxt, rewards = zip(*transitions)
+        slot, non_final = [], []
+        for s in nxt:
+            if s is None:
+                slot.append(-1)
+            else:
+                slot.append(len(non_final))
+                non_final.append(s)
+        return cls(Batch.from_data_list(states), torch.tensor([int(a) for a in actions], dtype=torch.int32),
+                   Batch.from_data_list(non_final) if non_final else None, torch.tensor(slot, dtype=torch.int32),
+                   torch.tensor([float(r) for r in rewards], dtype=torch.float32))
+
+    def pin_memory(self):
+        return ReplayBatch(self.states.pin_memory(), self.actions.pin_memory(),
+                           None if self.next_states is None else self.next_states.pin_memory(),
+                           self.next_slot.pin_memory(), self.rewards.pin_memory())
+
+    def to(self, device, non_blocking=True):
+        return ReplayBatch(self.states.to(device, non_blocking=non_blocking), self.actions.to(device, non_blocking=non_blocking),
+                           None if self.next_states is None else self.next_states.to(device, non_blocking=non_blocking),
+                           self.next_slot.to(device, non_blocking=non_blocking),
+                           self.rewards.to(device, non_blocking=non_blocking))
+
+    def h2d_bytes(self):
+        n = 0
+        for b in (self.states, self.next_states):
+            if b is None:
+                continue
+            n += b.x.numel() * b.x.element_size() + b.edge_index.numel() * 8 + b.ptr.numel() * 8 + b.eptr.numel() * 8 + \
+                b.batch.numel() * 8
+        return n + self.actions.numel() * 4 + self.next_slot.numel() * 4 + self.rewards.numel() * 4
+
+
+def multistep_lr(base_lr, step, milestones=(500000, 1000000, 1500000), gamma=0.1):
+    """optim.lr_scheduler.MultiStepLR as used at airfoil_dqn.py:175-176."""
+    return base_lr * gamma ** sum(1 for m in milestones if step >= m)
+
+
+class ReplayTrainer:
+    def __init__(self, policy_net_1, policy_net_2, lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50,
+                 betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        self.nets = (policy_net_1, policy_net_2)
+        self.lr, self.wd, self.gamma = float(lr), float(weight_decay), float(gamma)
+        self.betas, self.eps = betas, float(eps)
+        self.target_update = int(target_update)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.select = True
+        self.num_grads = 0
+        self._state = [None, None]
+        self.timers = None  # optional {name: [(start_event, end_event), ...]} for per-kernel timing
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _adam_state(self, i):
+        if self._state[i] is None:
+            net = self.nets[i]
+            net._ensure_packed()
+            z = torch.zeros_like(net._flat)
+            self._state[i] = dict(m=z, v=z.clone(), g=torch.zeros_like(net._flat), step=0)
+        return self._state[i]
+
+    def _timed(self, name):
+        tr = self
+
+        class _T:
+            def __enter__(self_inner):
+                if tr.timers is not None:
+                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e0.record()
+
+            def __exit__(self_inner, *a):
+                if tr.timers is not None:
+                    self_inner.e1.record()
+                    tr.timers.setdefault(name, []).append((self_inner.e0, self_inner.e1))
+
+        return _T()
+
+    # -- one replay step ----------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, batch: ReplayBatch):
+        """Returns the Huber loss (device scalar tensor); parameters of the selected net are updated."""
+        net1, net2 = self.nets
+        dev = batch.states.x.device
+        L = _lib.lib()
+        p = _lib.ptr
+        B = int(batch.actions.shape[0])
+        s_args = net1._prep(batch.states)
+        with self._timed("qnet_fwd"):
+            q1, _, _ = net1._launch_forward(*s_args, False, False)
+        if batch.next_states is not None:
+            n_args = net2._prep(batch.next_states)
+            with self._timed("qnet_fwd"):
+                q2, _, _ = net2._launch_forward(*n_args, False, False)
+            n_next = int(q2.shape[0])
+        else:
+            n_args, q2, n_next = None, None, 0
+        A = int(q1.shape[1])
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        sel = 0 if self.select else 1
+        gq = torch.empty((B if self.select else max(n_next, 1), A), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), self._timed("huber"):
+            rc = L.mdq_huber_replay(p(q1), p(q2), p(batch.actions), p(batch.rewards), p(batch.next_slot), B, n_next, A,
+                                    self.gamma, 1 if self.select else 0, p(loss), p(gq) if self.select else None,
+                                    None if self.select else p(gq), _lib.stream_ptr())
+        _lib.check(rc, "mdq_huber_replay")
+        net = self.nets[sel]
+        st = self._adam_state(sel)
+        if self.select or n_args is not None:
+            args = s_args if self.select else n_args
+            with self._timed("qnet_bwd+wgrad"):
+                net._launch_backward(*args, gq, st["g"])
+        else:
+            st["g"].zero_()
+        n_used = net._n_used
+        if self.world > 1:
+            with self._timed("allreduce"):
+                torch.distributed.all_reduce(st["g"][:n_used], group=self.pg)
+        st["step"] += 1
+        lr = multistep_lr(self.lr, self.num_grads)
+        with torch.cuda.device(dev), self._timed("adam"):
+            rc = L.mdq_adam_step(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0], self.betas[1],
+                                 self.eps, self.wd, 1.0 / self.world, st["step"], _lib.stream_ptr())
+        _lib.check(rc, "mdq_adam_step")
+        self.num_grads += 1
+        if self.num_grads % self.target_update == 0:
+            self.select = not self.select
+        return loss

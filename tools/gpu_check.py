@@ -29,9 +29,11 @@ def section(name):
 
 
 what = sys.argv[1:] or ["gnn", "bwd", "geom", "env"]
+import traceback
 
-if "gnn" in what:
+def run_gnn():
     section("GNN forward parity")
+    global net, g
     torch.manual_seed(1370)
     ref = gnn_ref.NodeRemovalNet(181, 128, 0.1)
     ref.set_num_nodes(17)
@@ -90,7 +92,7 @@ if "gnn" in what:
         t1.record(); torch.cuda.synchronize()
         print("fwd B=1: %.1f us/launch" % (t0.elapsed_time(t1) * 1000 / 20))
 
-if "bwd" in what:
+def run_bwd():
     section("GNN backward parity")
     torch.manual_seed(1370)
     ref = gnn_ref.NodeRemovalNet(181, 128, 0.1)
@@ -134,7 +136,7 @@ if "geom" in what or "env" in what:
     from oracle.env_ref import Env2DAirfoilRef
     from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
 
-if "geom" in what:
+def run_geom():
     section("geometry parity (ys930)")
     coords, cells, U, P = oracle_fields("ys930")
     cfg = make_config()
@@ -159,7 +161,7 @@ if "geom" in what:
           tuple(s.edge_index.shape))
     print("coord_map equal", env.coord_map == renv.coord_map)
 
-if "env" in what:
+def run_env():
     section("episode parity")
     for short in ("ys930", "ah93w145"):
         coords, cells, U, P = oracle_fields(short)
@@ -202,4 +204,11 @@ if "env" in what:
             if done or rdone:
                 break
         print(short, "steps", len(acts), "actions equal", acts == racts, "env step ms", 1000 * t_env / len(acts), "distinct actions", len(set(acts)))
+for name, fn in (("gnn", run_gnn), ("bwd", run_bwd), ("geom", run_geom), ("env", run_env)):
+    if name in what:
+        try:
+            fn()
+        except Exception:
+            traceback.print_exc()
+            torch.cuda.synchronize()
 print("\nlaunches", _lib.lib().mdq_launch_count())
