@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MeshDQN hot path on B200 (one process per GPU).
+
+Workload (BASELINE.json configs[2], the configuration the 1/2/4/8-GPU metric is quoted on):
+replay training on a minibatch of 256 ys930-sized state graphs PER GPU (weak scaling) with
+NodeRemovalNet(181, conv_width=128, topk=0.1): forward Q1(s), forward Q2(s'), Huber, backward,
+gradient all-reduce (NCCL, N>1), Adam.  A "step" is one such replay step; `value` = graphs
+(transitions) per second over all ranks with the batch resident in HBM; `e2e` = the same through
+ReplayBatch.to(device) from pinned host memory plus the loss read-back every step.
+Extras on the same JSON line: forward-only Q-evals, ys930 env steps, re-interpolation vertices/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--big]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+--impl reference times the CPU oracle restatement of the same replay step on the host cores (the
+reference stack -- torch_geometric + FEniCS -- cannot be installed offline).
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BATCH = 256
+METRIC = "replay_train_graphs_per_s"
+UNIT = "graphs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(n_gpus):
+    return {"workload": "replay training, 256 ys930-sized state graphs per GPU (BASELINE.json configs[2]): "
+                        "NodeRemovalNet(181,128,0.1) fwd Q1 + fwd Q2 + Huber + bwd + allreduce + Adam",
+            "graphs_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "nodes_per_graph": 180, "features": 17,
+            "parallelism": f"dp{n_gpus}", "l2": "256 MiB write between timed steps (L2 flush)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def harvest_transitions(make_env, n, seed):
+    """Seeded random-policy episodes (epsilon = 1 branch of airfoil_dqn.py:455-459) -> n transitions on the host."""
+    rng = np.random.RandomState(seed)
+    out = []
+    while len(out) < n:
+        with quiet():
+            env = make_env()
+            s = env.get_state()
+            for _ in range(60):
+                a = int(rng.randint(0, env.N_CLOSEST + 1))
+                s2, r, done, _ = env.step(a)
+                out.append((s.to("cpu"), a, None if done else s2.to("cpu"), float(r)))
+                s = s2
+                if done or len(out) >= n:
+                    break
+    return out[:n]
+
+
+def env_factory(device=None):
+    from conftest import make_config, oracle_fields
+    coords, cells, U, P = oracle_fields("ys930")
+    cfg = make_config()
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    if device is None:
+        from oracle.env_ref import Env2DAirfoilRef
+        return lambda: Env2DAirfoilRef(cfg, mesh=(coords, cells))
+    from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
+    return lambda: Env2DAirfoil(cfg, mesh=(coords, cells), device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle restatement of the same replay step
+# --------------------------------------------------------------------------------------------------
+def cpu_replay_steps(transitions, max_seconds, max_steps, warmup):
+    from meshdqn_b200.replay import ReplayBatch
+    from oracle import gnn_ref
+    rb = ReplayBatch.from_transitions(transitions)
+    torch.manual_seed(1370)
+    nets = []
+    for _ in range(2):
+        n = gnn_ref.NodeRemovalNet(181, 128, 0.1)
+        n.set_num_nodes(17)
+        nets.append(n)
+    opt = torch.optim.Adam(nets[0].parameters(), lr=1e-5, weight_decay=1e-6)
+    mask = rb.next_slot >= 0
+
+    def step():
+        opt.zero_grad()
+        loss = gnn_ref.replay_loss(nets[0], nets[1], rb.states, rb.actions.long(), (rb.next_states, mask), rb.rewards, 1.0, True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    k = 0
+    while k < max_steps and (time.perf_counter() - t0) < max_seconds:
+        step()
+        k += 1
+    dt = time.perf_counter() - t0
+    return k, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tr = harvest_transitions(env_factory(None), BATCH, 1000)
+    k, dt = cpu_replay_steps(tr, max_seconds=120.0, max_steps=args.steps, warmup=min(args.warmup, 2))
+    val = BATCH * k / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": min(args.warmup, 2),
+            "ms_per_step": 1000 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{k} replay steps of the {BATCH}-graph batch, CPU oracle (torch fp32 restatement of PyG)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "torch_geometric/FEniCS cannot be installed offline; the reference arm is the CPU oracle port"}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from meshdqn_b200 import _lib
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    from meshdqn_b200.parallel import init_from_env, max_over_ranks
+    from meshdqn_b200.replay import ReplayBatch, ReplayTrainer
+    import torch.distributed as dist
+
+    rank, local, world = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    K, W = args.steps, max(args.warmup, 3)
+
+    tr = harvest_transitions(env_factory(dev), BATCH, 1000 + rank)
+    rb_host = ReplayBatch.from_transitions(tr).pin_memory()
+    rb_dev = rb_host.to(dev)
+    torch.manual_seed(1370)
+    nets = []
+    for _ in range(2):
+        n = NodeRemovalNet(181, conv_width=128, topk=0.1)
+        n.set_num_nodes(17)
+        nets.append(n.to(dev))
+    trainer = ReplayTrainer(nets[0], nets[1], lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        trainer.step(rb_dev)
+    barrier()
+    # ---- timed: K steps, inputs resident in HBM, L2 flushed between steps, CUDA events per step ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    l0 = L.mdq_launch_count()
+    with ClockSampler(local) as clk:
+        barrier()
+        for e0, e1 in evs:
+            flush.fill_(1)
+            e0.record()
+            trainer.step(rb_dev)
+            e1.record()
+        barrier()
+    launches = int(L.mdq_launch_count() - l0)
+    ms_local = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    ms_total = max_over_ranks(ms_local, dev)
+    ms_step = ms_total / K
+    value = world * BATCH / (ms_step * 1e-3)
+
+    # ---- e2e: pinned host batch -> device, step, loss read-back, every step ----
+    for _ in range(2):
+        float(trainer.step(rb_host.to(dev)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        float(trainer.step(rb_host.to(dev)))
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_val = world * BATCH * K / e2e_s
+
+    # ---- per-kernel durations (CUDA events around each launch group) for the roofline object ----
+    trainer.timers = {}
+    for _ in range(K):
+        flush.fill_(1)
+        trainer.step(rb_dev)
+    torch.cuda.synchronize()
+    kern = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) * 1e3 for k, v in trainer.timers.items()}  # us per launch
+    trainer.timers = None
+
+    line = None
+    if rank == 0:
+        hbm, how = peaks()
+        n_nodes = int(rb_dev.states.x.shape[0])
+        n_edges = int(rb_dev.states.edge_index.shape[1])
+        net = nets[0]
+        # algorithmic bytes of the dominant kernel (backward = recompute + gradients): inputs once, parameters once,
+        # gradient written once (DESIGN.md "Algorithmic bytes")
+        alg_bytes = 4 * n_nodes * 17 + 16 * n_edges + 8 * (BATCH + 1) + 4 * BATCH * 181 + 2 * 4 * net._n_used
+        dom = "qnet_bwd+wgrad"
+        dom_us = kern.get(dom, float("nan"))
+        achieved = alg_bytes / (dom_us * 1e-6) / 1e9
+        extras = {}
+        if not args.no_extras:
+            extras = measure_extras(dev, nets[0], rb_dev, flush, args)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world), "clocks": clk.summary(),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rb_host.h2d_bytes()), "d2h_bytes_per_step": 4},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "qnet_kernel<bwd> + wgrad_partial + wgrad_reduce", "achieved": achieved,
+                             "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": dom_us,
+                             "note": "launch/latency-bound at 256 x 180-node graphs (15 KB per graph); see DESIGN.md"},
+                "kernel_us": kern, "extras": extras}
+        if world == 1 and not args.no_cpu:
+            k, dt = cpu_replay_steps(tr, max_seconds=15.0, max_steps=1000, warmup=1)
+            line["cpu_baseline"] = {"value": BATCH * k / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{k} replay steps of the same {BATCH}-graph batch in {dt:.1f} s, CPU oracle (torch fp32)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_events(fn, iters, flush=None):
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters  # ms
+
+
+def measure_extras(dev, net, rb_dev, flush, args):
+    """Secondary numbers of BASELINE.json's metric: Q-eval graphs/s, ys930 env steps/s, re-interp vertices/s."""
+    from meshdqn_b200.Env2DAirfoil import SourceField
+    from meshdqn_b200.flow_solver import DeviceMesh
+    from meshdqn_b200.synthetic import synthetic_airfoil_mesh, synthetic_fields
+    hbm, _ = peaks()
+    out = {}
+    with torch.no_grad():
+        sargs = net._prep(rb_dev.states)
+        f = lambda: net._launch_forward(*sargs, False, True)
+        for _ in range(3):
+            f()
+        ms = time_events(f, 20, flush)
+        out["q_eval_b256"] = {"graphs_per_s": BATCH / (ms * 1e-3), "us_per_launch": ms * 1e3}
+        from meshdqn_b200.data import Data
+        n0 = int(rb_dev.states.ptr[1])
+        e0 = int(rb_dev.states.eptr[1])
+        one = Data(x=rb_dev.states.x[:n0].contiguous(), edge_index=rb_dev.states.edge_index[:, :e0].contiguous())
+        oargs = net._prep(one)
+        f1 = lambda: net._launch_forward(*oargs, False, True)
+        for _ in range(3):
+            f1()
+        ms = time_events(f1, 20, None)
+        out["q_eval_b1"] = {"graphs_per_s": 1.0 / (ms * 1e-3), "us_per_launch": ms * 1e3}
+    # ys930 episode steps (Qhull on the host inside, as in the reference)
+    mk = env_factory(dev)
+    with quiet():
+        env = mk()
+        s = env.get_state()
+        rng = np.random.RandomState(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(30):
+            am, _ = net.select_action(s)
+            s, r, done, _ = env.step(int(rng.randint(0, 180)))
+            n += 1
+            if done:
+                break
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        m1 = env.flow_solver.mesh
+        fi = lambda: env.source.interpolate(m1)
+        for _ in range(3):
+            fi()
+        ms = time_events(fi, 20, flush)
+    out["env_step_ys930"] = {"steps_per_s": n / dt, "ms_per_step": 1e3 * dt / n, "note": "Q-eval + Qhull (host) + device step"}
+    npt = m1.nv + m1.ne
+    out["reinterp_ys930"] = {"vertices_per_s": npt / (ms * 1e-3), "us_per_launch": ms * 1e3, "target_points": npt, "T": 5}
+    # large synthetic mesh: full-field re-interpolation onto a coarsened copy (throughput mode, no smoothing)
+    ntri = 1_000_000 if args.big else 250_000
+    coords, cells, _ = synthetic_airfoil_mesh(ntri, seed=0)
+    m0 = DeviceMesh(coords, cells, dev)
+    U0, P0 = synthetic_fields(coords, m0.edges.cpu().numpy(), 5, 0)
+    src = SourceField(m0, U0, P0)
+    from scipy.spatial import Delaunay
+    rng = np.random.RandomState(1)
+    isb = m0.on_boundary.cpu().numpy().astype(bool)
+    drop = rng.choice(np.nonzero(~isb)[0], max(1, len(coords) // 100), replace=False)
+    keep = np.ones(len(coords), bool)
+    keep[drop] = False
+    c2 = coords[keep]
+    t2 = Delaunay(c2).simplices
+    b2 = isb[keep]
+    t2 = t2[b2[t2].sum(1) != 3]
+    m2 = DeviceMesh(c2, t2, dev)
+    fi = lambda: src.interpolate(m2)
+    for _ in range(3):
+        fi()
+    ms = time_events(fi, 10, flush)
+    npt = m2.nv + m2.ne
+    # algorithmic bytes: target vertices + edge list, source coords/cells/cell->dof map, source
+    # coefficients, written dofs + cell ids
+    T = 5
+    alg = 16 * m2.nv + 8 * m2.ne + 16 * m0.nv + 36 * m0.nc + 8 * T * (2 * (m0.nv + m0.ne) + m0.nv) + \
+        8 * T * (2 * npt + m2.nv) + 4 * npt
+    out["reinterp_synthetic"] = {"triangles": int(m0.nc), "target_points": npt, "vertices_per_s": npt / (ms * 1e-3),
+                                 "ms_per_launch": ms, "algorithmic_bytes": alg, "achieved_GBps": alg / (ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / hbm, "bin_entries": src.n_bin_entries,
+                                 "grid": [src.gx, src.gy]}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--big", action="store_true", help="use the ~1M-triangle synthetic mesh for the re-interpolation extra")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

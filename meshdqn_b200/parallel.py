@@ -1,0 +1,52 @@
+"""Data-parallel plumbing for replay training: one process per GPU, torch.distributed (NCCL).
+
+Graphs are independent, so the replay minibatch shards by graph with no data-path collective
+(SURVEY.md 8e); the single exchange is an all-reduce of the flat fp32 gradient.  These helpers are
+backend-agnostic so the host logic is tested on CPU with gloo (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous [lo, hi) slice of n items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's RANK / WORLD_SIZE / MASTER_* variables."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def allreduce_mean_(flat: torch.Tensor, world: int, group=None):
+    """In-place mean over ranks of a flat gradient buffer (sum all-reduce, then scale)."""
+    if world > 1:
+        dist.all_reduce(flat, group=group)
+        flat.mul_(1.0 / world)
+    return flat
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Max of a scalar over ranks (used for device-timed multi-GPU measurements)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

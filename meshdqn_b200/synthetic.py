@@ -48,8 +48,11 @@ def synthetic_fields(coords, edges, T=5, seed=0):
     return np.ascontiguousarray(u), np.ascontiguousarray(p[:, : len(coords)])
 
 
-def _naca_ring(n, chord=1.0, t=0.12, m=0.02, pc=0.4, x0=0.0, y0=0.0):
-    """Closed NACA 4-digit contour, n points in curve order (upper TE->LE, lower LE->TE)."""
+def _naca_ring(n, chord=1.0, t=0.12, m=0.0, pc=0.4, x0=0.0, y0=0.0):
+    """Closed NACA 4-digit contour, n points in curve order (upper TE->LE, lower LE->TE).
+
+    Symmetric (convex) by default: every Delaunay cell with three ring vertices then lies inside the
+    airfoil, so the reference's all-boundary-cell rule removes exactly the hole."""
     nu = n // 2 + 1
     beta = np.linspace(0.0, np.pi, nu)
     xc = 0.5 * (1 + np.cos(beta))  # 1 -> 0
@@ -62,6 +65,12 @@ def _naca_ring(n, chord=1.0, t=0.12, m=0.02, pc=0.4, x0=0.0, y0=0.0):
     xl = xl[: n - nu]
     lo = np.stack([xl, camber(xl) - thick(xl)], 1)
     ring = np.concatenate([up, lo], 0)[:n]
+    # re-sample uniformly in arc length (cosine clustering would create micron-sized edges at 1M cells)
+    closed = np.concatenate([ring, ring[:1]], 0)
+    seg = np.sqrt((np.diff(closed, axis=0) ** 2).sum(1))
+    s_acc = np.concatenate([[0.0], np.cumsum(seg)])
+    s_new = np.linspace(0.0, s_acc[-1], n + 1)[:-1]
+    ring = np.stack([np.interp(s_new, s_acc, closed[:, 0]), np.interp(s_new, s_acc, closed[:, 1])], 1)
     ring[:, 0] = ring[:, 0] * chord + x0
     ring[:, 1] = ring[:, 1] * chord + y0
     return ring
@@ -91,11 +100,21 @@ def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None):
         np.stack([xs, np.full_like(xs, -0.5)], 1), np.stack([xs, np.full_like(xs, 0.5)], 1),
         np.stack([np.full_like(ys, -0.5), ys], 1), np.stack([np.full_like(ys, 3.0), ys], 1)])
     nb = 4 + len(ring) + len(walls)
-    n_int = max(16, nv_target - nb)
+    # one buffer layer of interior points facing every wall edge, so that no Delaunay cell has three
+    # outer-boundary vertices (the reference's drop rule would otherwise notch the corners)
+    xm = 0.5 * (np.linspace(-0.5, 3.0, nx + 1)[1:] + np.linspace(-0.5, 3.0, nx + 1)[:-1])
+    ym = 0.5 * (np.linspace(-0.5, 0.5, ny + 1)[1:] + np.linspace(-0.5, 0.5, ny + 1)[:-1])
+    off = 0.75 * h_wall
+    ym_in = ym[(ym > -0.5 + 1.2 * off) & (ym < 0.5 - 1.2 * off)]
+    buffer_pts = np.concatenate([
+        np.stack([xm, np.full_like(xm, -0.5 + off)], 1), np.stack([xm, np.full_like(xm, 0.5 - off)], 1),
+        np.stack([np.full_like(ym_in, -0.5 + off), ym_in], 1), np.stack([np.full_like(ym_in, 3.0 - off), ym_in], 1)])
+    n_int = max(16, nv_target - nb - len(buffer_pts))
     # graded interior cloud: rejection-sample density ~ 1/h^2, h = h0 + a*dist(chord)
     pts = []
     got = 0
-    h0, a = 0.02, 1.0
+    h0, a = 0.05, 0.6
+    acc_rate = 0.05
     # polygon test helpers (ring is a simple polygon)
     def inside_ring(q):
         xq, yq = q[:, 0], q[:, 1]
@@ -109,7 +128,7 @@ def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None):
             ins ^= cond & (xq < xi)
         return ins
     while got < n_int:
-        m = int((n_int - got) * 3) + 1024
+        m = min(int((n_int - got) / acc_rate * 1.3) + 1024, 8_000_000)
         q = np.stack([rng.uniform(-0.5, 3.0, m), rng.uniform(-0.5, 0.5, m)], 1)
         dx = np.clip(q[:, 0], 0.0, 1.0) - q[:, 0]
         d = np.sqrt(dx ** 2 + q[:, 1] ** 2)
@@ -117,22 +136,33 @@ def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None):
         acc = rng.uniform(0, 1, m) < (h0 / h) ** 2
         q = q[acc]
         # keep points clear of the hole and of the boundaries
-        near = (q[:, 0] > -0.05) & (q[:, 0] < 1.05) & (np.abs(q[:, 1]) < 0.2)
+        xq = np.clip(q[:, 0], 0.0, 1.0)
+        yt = 5 * 0.12 * (0.2969 * np.sqrt(xq) - 0.1260 * xq - 0.3516 * xq ** 2 + 0.2843 * xq ** 3 - 0.1036 * xq ** 4)
+        band = 4.0 * (2.05 / n_af)
+        near = (q[:, 0] > -band) & (q[:, 0] < 1.0 + band) & (np.abs(q[:, 1]) < yt + band)
         bad = np.zeros(len(q), dtype=bool)
         if near.any():
             qn = q[near]
             insn = inside_ring(qn)
-            # distance to ring vertices as a cheap clearance test
-            step = max(1, len(ring) // 256)
-            rr = ring[::step]
-            dmin = np.sqrt(((qn[:, None, :] - rr[None, :, :]) ** 2).sum(-1)).min(1) if len(qn) < 200000 else \
-                np.full(len(qn), 1.0)
-            bad[np.nonzero(near)[0]] = insn | (dmin < 0.5 * (2.2 / n_af))
-        bad |= (q[:, 0] < -0.5 + 0.5 * h_wall) | (q[:, 0] > 3.0 - 0.5 * h_wall) | (np.abs(q[:, 1]) > 0.5 - 0.5 * h_wall)
+            # clearance: distance to the ring segments must exceed 0.7 ring spacings, so no point sits in
+            # the diametral circle of a ring edge and the contour stays in the Delaunay triangulation
+            ax, ay = ring[:, 0], ring[:, 1]
+            bx, by = np.roll(ax, -1), np.roll(ay, -1)
+            ex, ey = bx - ax, by - ay
+            l2 = ex * ex + ey * ey
+            dmin = np.full(len(qn), np.inf)
+            for lo in range(0, len(qn), 4096):
+                qq = qn[lo:lo + 4096]
+                tt = np.clip(((qq[:, None, 0] - ax) * ex + (qq[:, None, 1] - ay) * ey) / l2, 0.0, 1.0)
+                dd = (ax + tt * ex - qq[:, None, 0]) ** 2 + (ay + tt * ey - qq[:, None, 1]) ** 2
+                dmin[lo:lo + 4096] = np.sqrt(dd.min(1))
+            bad[np.nonzero(near)[0]] = insn | (dmin < 0.7 * (2.05 / n_af))
+        bad |= (q[:, 0] < -0.5 + 1.5 * h_wall) | (q[:, 0] > 3.0 - 1.5 * h_wall) | (np.abs(q[:, 1]) > 0.5 - 1.5 * h_wall)
         q = q[~bad]
+        acc_rate = max(1e-3, len(q) / m)
         pts.append(q)
         got += len(q)
-    interior = np.concatenate(pts, 0)[:n_int]
+    interior = np.concatenate([buffer_pts] + pts, 0)[:n_int + len(buffer_pts)]
     coords = np.concatenate([corners, ring, walls, interior], 0)
     tri = Delaunay(coords)
     cells = tri.simplices

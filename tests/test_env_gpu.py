@@ -1,0 +1,159 @@
+"""GPU parity: the per-action environment step (through the C-ABI) vs the CPU oracle and golden episodes.
+
+Bars (BASELINE.json north_star): point-location cell indices, removable masks and the chosen action
+bit-exact; interpolated fields and drag/lift within 1e-10 relative in float64.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, lively_state_dict, load_mesh, make_config, oracle_fields
+from oracle import geom, gnn_ref
+from oracle.env_ref import Env2DAirfoilRef
+
+pytestmark = pytest.mark.gpu
+
+
+def checksum(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], dtype=np.int64)[0]
+
+
+def make_envs(short, dev, **kw):
+    from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
+    coords, cells, U, P = oracle_fields(short)
+    cfg = make_config(**kw)
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    return Env2DAirfoil(cfg, mesh=(coords, cells), device=dev), Env2DAirfoilRef(cfg, mesh=(coords, cells))
+
+
+@pytest.mark.parametrize("short", ["ys930", "ah93w145"])
+def test_mesh_services_bit_exact(cuda_device, short):
+    env, renv = make_envs(short, cuda_device)
+    m, rt = env.flow_solver.mesh, renv.flow_solver.topo
+    assert (m.ne, m.nb) == (rt.ne, len(rt.boundary_vertices))
+    assert np.array_equal(m.edges.cpu().numpy(), rt.edges)
+    assert np.array_equal(m.cell_edges.cpu().numpy(), rt.cell_edges)
+    assert np.array_equal(m.nbr_ptr.cpu().numpy(), rt.nbr_ptr) and np.array_equal(m.nbr_idx[: 2 * m.ne].cpu().numpy(), rt.nbr_idx)
+    assert np.array_equal(m.vc_idx.cpu().numpy(), rt.vc_idx)
+    assert np.array_equal(m.boundary_vertices(), rt.boundary_vertices)
+    assert np.array_equal(m.coordinates(), renv.flow_solver.coords)          # 50 Gauss-Seidel sweeps, bit-identical
+    assert np.array_equal(env.flow_solver.tags.cpu().numpy(), renv.flow_solver.tags)
+    assert np.array_equal(env.flow_solver.removable, renv.flow_solver.removable)
+    assert np.array_equal(env.distance_lookup, renv.distance_lookup)
+    assert np.abs(env.gt_drag / renv.gt_drag - 1).max() < 1e-10 and np.abs(env.gt_lift / renv.gt_lift - 1).max() < 1e-10
+    z = np.load(os.path.join(GOLDEN, f"episode_{short}.npz"))
+    assert np.array_equal(m.coordinates(), z["coords_smoothed"]) and np.array_equal(env.flow_solver.removable, z["removable"])
+    assert np.array_equal(env.flow_solver.tags.cpu().numpy(), z["tags"])
+    s = env.get_state()
+    assert np.array_equal(s.x.cpu().numpy(), z["x0"]) and np.array_equal(s.edge_index.cpu().numpy(), z["edge_index0"])
+    renv.get_state()
+    assert env.coord_map == renv.coord_map and env.inv_coord_map == renv.inv_coord_map
+    assert np.array_equal(env.n_closest, renv.n_closest)
+
+
+@pytest.mark.parametrize("short", ["ys930", "ah93w145"])
+def test_greedy_episode_matches_oracle_and_golden(cuda_device, short):
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    env, renv = make_envs(short, cuda_device)
+    z = np.load(os.path.join(GOLDEN, f"episode_{short}.npz"))
+    torch.manual_seed(1370)
+    ref = gnn_ref.NodeRemovalNet(181, 128, 0.1)
+    ref.set_num_nodes(17)
+    ref.load_state_dict(lively_state_dict(ref))
+    net = NodeRemovalNet(181, 128, 0.1)
+    net.set_num_nodes(17)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(cuda_device)
+    s, rs = env.get_state(), renv.get_state()
+    acts = []
+    for i in range(len(z["actions"])):
+        am, q = net.select_action(s)
+        a = int(am[0])
+        with torch.no_grad():
+            ra = int(ref(rs).argmax())
+        assert a == ra == int(z["actions"][i]), f"step {i}"
+        s, r, done, _ = env.step(a)
+        rs, rr, rdone, _ = renv.step(ra)
+        acts.append(a)
+        assert done == rdone == bool(z["dones"][i])
+        assert abs(r - rr) < 1e-9 and abs(r - z["rewards"][i]) < 1e-9
+        if a != env.action_space.n:
+            cell_of = env.last["cell_of"].cpu().numpy()
+            assert np.array_equal(cell_of, renv.last["cell_of"])                       # bit-exact point location
+            assert checksum(cell_of) == z["cell_checksums"][i]
+            assert int(env.last["miss"]) == renv.last["nmiss"]
+            U, rU = env.U.cpu().numpy(), renv.U
+            assert np.abs(U - rU).max() <= 1e-10 * np.abs(rU).max()
+            assert np.abs(env.P.cpu().numpy() - renv.P).max() <= 1e-10 * np.abs(renv.P).max()
+        assert np.array_equal(env.flow_solver.removable, renv.flow_solver.removable)
+        assert np.abs(env.new_drags / renv.new_drags - 1).max() < 1e-10
+        assert np.abs(env.new_lifts / renv.new_lifts - 1).max() < 1e-10
+        assert np.abs(env.new_drags / z["drags"][i] - 1).max() < 1e-10
+        assert torch.equal(s.x.cpu(), rs.x) and torch.equal(s.edge_index.cpu(), rs.edge_index)
+        assert env.flow_solver.mesh.nv == z["nvs"][i]
+        if done:
+            break
+    assert done and len(acts) == len(z["actions"])
+    assert np.array_equal(s.x.cpu().numpy(), z["x_last"])
+
+
+def test_do_nothing_action_and_attributes(cuda_device):
+    env, renv = make_envs("ys930", cuda_device)
+    n = env.action_space.n
+    assert n == 180 and env.N_CLOSEST == 180 and len(env.coord_map) == 180
+    s, r, done, info = env.step(n)          # do nothing: window shifts by one (quirk B5), reward recomputed
+    rs, rr, rdone, _ = renv.step(n)
+    assert env.do_nothing_offset == 1 and info == {} and not done
+    assert abs(r - rr) < 1e-12 and abs(r - 1.0) < 1e-9   # unchanged mesh: drag error 0 -> reward 2*exp(0)-1
+    assert torch.equal(s.x.cpu(), rs.x) and torch.equal(s.edge_index.cpu(), rs.edge_index)
+    assert env.velocities.shape == (5, 876, 2) and env.pressures.shape == (5, 876, 1)
+    assert np.array_equal(env.velocities, renv.velocities) and np.array_equal(env.pressures, renv.pressures)
+    assert env.return_vals()[0] is env.gt_drag
+    d = float(env.flow_solver.drag_probe.sample(env.U[0], env.P[0]))
+    assert abs(d / renv.gt_drag[0] - 1) < 1e-10
+
+
+def test_interpolation_on_synthetic_mesh_with_random_removals(cuda_device):
+    """Size-independent properties on a larger synthetic mesh: P2 interpolation reproduces quadratics exactly,
+    cell indices equal the oracle's brute-force search, repeated runs are bit-identical."""
+    from meshdqn_b200.Env2DAirfoil import SourceField
+    from meshdqn_b200.flow_solver import DeviceMesh
+    from meshdqn_b200.synthetic import synthetic_airfoil_mesh
+    from scipy.spatial import Delaunay
+    coords, cells, _ = synthetic_airfoil_mesh(20000, seed=1)
+    topo0 = geom.Topology(cells, len(coords))
+    pts2 = topo0.p2_points(coords)
+    f = lambda p: np.stack([1 + p[:, 0] ** 2 - p[:, 0] * p[:, 1], 2 * p[:, 1] ** 2 + p[:, 0]], 1)
+    U0 = np.stack([f(pts2), -f(pts2)])
+    P0 = np.stack([3 * coords[:, 0] - coords[:, 1], coords[:, 0] + 1])
+    m0 = DeviceMesh(coords, cells, cuda_device)
+    src = SourceField(m0, U0, P0)
+    rng = np.random.RandomState(0)
+    interior = np.nonzero(~topo0.on_boundary)[0]
+    drop = rng.choice(interior, 200, replace=False)
+    keep = np.ones(len(coords), bool)
+    keep[drop] = False
+    c2 = coords[keep]
+    newid = np.cumsum(keep) - 1
+    isb = np.zeros(len(c2), bool)
+    isb[newid[topo0.boundary_vertices]] = True
+    t2 = Delaunay(c2).simplices
+    t2 = t2[isb[t2].sum(1) != 3]
+    m1 = DeviceMesh(c2, t2, cuda_device)
+    U, P, cell_of, miss = src.interpolate(m1)
+    topo1 = geom.Topology(t2, len(c2))
+    pts = topo1.p2_points(c2)
+    ref_cells, nmiss, _ = geom.locate(pts, coords, topo0.cells)
+    assert np.array_equal(cell_of.cpu().numpy(), ref_cells) and int(miss) == nmiss
+    inside = np.ones(len(pts), bool)
+    if nmiss:
+        inside = geom.locate(pts, coords, topo0.cells)[2] == 0
+    Un = U.cpu().numpy()
+    assert np.abs(Un[0][inside] - f(pts)[inside]).max() < 1e-11      # exact for quadratics
+    assert np.abs(P.cpu().numpy()[0] - (3 * c2[:, 0] - c2[:, 1]))[inside[: len(c2)]].max() < 1e-11
+    assert np.array_equal(Un[1], -Un[0])                              # linearity, bit-exact
+    U2, P2, cell2, _ = src.interpolate(m1)
+    assert torch.equal(U2, U) and torch.equal(P2, P) and torch.equal(cell2, cell_of)
