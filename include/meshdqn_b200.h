@@ -85,6 +85,10 @@ int mdq_qnet_forward(const mdq_net_t *net, const float *params, const float *x, 
                      const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
                      int max_n, int max_e, float *out, float *embedding, int32_t *argmax, void *stream);
 
+/* Profiling aid: when set (device int64[128], NULL to disable), CTA 0 of the next qnet launches writes clock64()
+ * at its phase boundaries (see MDQ_TRACE in csrc/gnn_fused.cu). */
+void mdq_qnet_set_trace(int64_t *device_buf);
+
 /* Rows of (delta, input) pairs the backward kernel emits for the weight-gradient pass. */
 int64_t mdq_qnet_bwd_workspace_floats(const mdq_net_t *net, int n_graphs, int max_n);
 
@@ -134,11 +138,12 @@ int mdq_mesh_topology(const int32_t *cells, int nc, int nv, int32_t *nbr_ptr, in
                       void *stream);
 
 /* Mesh.smooth(iters) (flow_solver.py:67,237): in-place Gauss-Seidel sweep in vertex order, boundary fixed.
- * The exact sweep order is kept by level-scheduling the vertex dependency DAG inside one CTA.
- * level [nv] i32 scratch. */
-int mdq_mesh_smooth(double *coords, int nv, const int32_t *nbr_ptr, const int32_t *nbr_idx, const int32_t *vc_ptr,
-                    const int32_t *vc_idx, const int32_t *cells, const uint8_t *on_boundary, int iters, int32_t *level,
-                    void *stream);
+ * The exact sequential result is kept by level-scheduling the vertex dependency DAG inside one CTA (8 lanes per
+ * vertex, coordinates + adjacency in shared memory); the ~depth*iters dependent updates bound its latency.
+ * status: device int32, set to 0 on completion. */
+int mdq_mesh_smooth(double *coords, int nv, int nc, const int32_t *nbr_ptr, const int32_t *nbr_idx,
+                    const int32_t *vc_ptr, const int32_t *vc_idx, const int32_t *cells, const uint8_t *on_boundary,
+                    int iters, int32_t *status, void *stream);
 
 /* FlowSolver.mark_boundaries (flow_solver.py:9-30,194-226): tags [ne] i32 (4 default, 0 walls, 1 airfoil,
  * 2 inflow, 3 outflow) and the removable mask (flow_solver.py:75-78,247-250; numpy `coord not in B`) [nv] u8. */

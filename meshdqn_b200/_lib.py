@@ -81,6 +81,7 @@ _SIGS = {
     "mdq_last_error": (ctypes.c_char_p, []),
     "mdq_version": (c_int, []),
     "mdq_launch_count": (c_int64, []),
+    "mdq_qnet_set_trace": (None, [_P]),
     "mdq_qnet_smem_bytes": (c_int64, [POINTER(mdq_net_t), c_int, c_int, c_int, c_int]),
     "mdq_qnet_pick_gpc": (c_int, [POINTER(mdq_net_t), c_int, c_int, c_int]),
     "mdq_qnet_forward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
@@ -90,7 +91,7 @@ _SIGS = {
     "mdq_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "mdq_scan_i32": (c_int, [_P, _P, c_int, _P]),
     "mdq_mesh_topology": (c_int, [_P, c_int, c_int] + [_P] * 14),
-    "mdq_mesh_smooth": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
+    "mdq_mesh_smooth": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     "mdq_mesh_tags_removable": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, _P, _P, _P]),
     "mdq_polygon_distance": (c_int, [_P, _P, c_int, _P, c_int, _P, _P]),
     "mdq_grid_count": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P]),

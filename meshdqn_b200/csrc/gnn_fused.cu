@@ -22,6 +22,9 @@ constexpr int NWARP = NT / 32;
 constexpr int MAXB = MDQ_MAX_BLOCKS;
 constexpr int MLP_SPLIT = 4;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_STAGE = 8;
+constexpr int STAGE_WORDS = 4096;  // 16 KB per stage
+constexpr int MAXCH = 128;
 
 struct QLay {
     int G, n_max, e_max, KC1, W, nb, bwd;
@@ -32,8 +35,18 @@ struct QLay {
     int xrows, e2cap, nrow_all, ymax;
     int o_w1, o_cat1, o_big, o_cat2, o_xbuf, o_hbuf, o_e1s, o_e1d, o_csr, o_e2s, o_e2d;
     int o_rowptr, o_cursor, o_score, o_z, o_newid, o_parent, o_dis, o_seg, o_ecnt, o_racc, o_y, o_part;
-    int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds, o_h1k;
+    int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds, o_h1k, o_c1k;
+    // weight stream: blocks >= 1 and the MLP read their weights from 16 KB shared-memory stages that one
+    // thread fills with cp.async.bulk (TMA) in layer order, several chunks ahead of the consumers
+    int nstage, o_stage[MAX_STAGE], o_mbar, nchunks;
+    int ck_blk[MAXB], ck_lin[3], ck_blin[3], ck_bblk[MAXB];
     int total;  // 4-byte words
+};
+
+struct WChunks {
+    int off[MAXCH];              // float offset into the flat parameter buffer
+    unsigned short rows[MAXCH];  // weight rows (k values) in the chunk
+    unsigned short cols[MAXCH];  // row length (outputs)
 };
 
 struct WLayer {
@@ -59,6 +72,8 @@ struct QArgs {
     const float *gout;
     float *ws;
     WDesc wd;
+    WChunks ck;
+    long long *trace;  // optional: clock64() of CTA 0 / thread 0 at phase boundaries (profiling aid)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -66,7 +81,7 @@ struct QArgs {
 // ------------------------------------------------------------------------------------------------
 int topk_count(float ratio, int n) { return (int)ceilf(ratio * (float)n); }
 
-int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLay &L)
+int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck = nullptr)
 {
     memset(&L, 0, sizeof(L));
     if (net.n_blocks < 1 || net.n_blocks > MAXB) return MDQ_EINVAL;
@@ -114,14 +129,26 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     const int dcat_words = dcat_a > dcat_c ? dcat_a : dcat_c;
     int alias_words = mdq::pad4(gcap1 * 2 * W);
     if (bwd) alias_words += mdq::pad4(L.xrows * W) + mdq::pad4(gcap1 * W) + mdq::pad4(dcat_words);
-    L.o_big = take(max_n * W > alias_words ? max_n * W : alias_words);
+    // the dense stages of blocks >= 1 give every thread one 4x4 output tile
+    if (((gcap1 + 3) / 4) * (W / 4) > NT) return MDQ_ESMEM;
+    const int big_words = mdq::pad4(max_n * W > alias_words ? max_n * W : alias_words);
+    L.o_big = take(big_words);
     L.o_cat2 = L.o_big;
     if (bwd) {
         L.o_dx = L.o_cat2 + mdq::pad4(gcap1 * 2 * W);
         L.o_dp = L.o_dx + mdq::pad4(L.xrows * W);
         L.o_dcat = L.o_dp + mdq::pad4(gcap1 * W);
-        L.o_h1k = take(gcap1 * W);  // block 0's kept hidden rows, saved before `big` is reused
+        L.o_h1k = take(gcap1 * W);      // block 0's kept hidden rows, saved before `big` is reused
+        L.o_c1k = take(gcap1 * L.KC1);  // ... and their input rows [agg | x]
     }
+    // weight-stream stages reuse what block 0 no longer needs: conv1's staged weights, cat1, the tail of `big`
+    L.nstage = 0;
+    if ((L.KC1 + 1) * W >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_w1;
+    if (max_n * L.KC1 >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_cat1;
+    for (int at = L.o_big + alias_words; at + STAGE_WORDS <= L.o_big + big_words && L.nstage < MAX_STAGE; at += STAGE_WORDS)
+        L.o_stage[L.nstage++] = at;
+    while (L.nstage < 2) L.o_stage[L.nstage++] = take(STAGE_WORDS);
+    L.o_mbar = take(2 * MAX_STAGE);
     L.o_xbuf = take(L.xrows * W);
     L.o_hbuf = take((bwd ? L.xrows : gcap1) * W);
     L.o_e1s = take(L.e_max);
@@ -148,6 +175,33 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
         L.o_tds = take(gcap1 * 2);
     }
     L.total = o;
+    // ---- weight chunks in consumption order ----
+    int nck = 0;
+    bool overflow = false;
+    auto add_layer = [&](int w_off, int K, int C) {
+        const int start = nck;
+        int per = (STAGE_WORDS / C) & ~3;
+        if (per < 4) { overflow = true; return start; }
+        for (int k0 = 0; k0 < K; k0 += per) {
+            if (nck >= MAXCH) { overflow = true; return start; }
+            if (ck) {
+                ck->off[nck] = w_off + k0 * C;
+                ck->rows[nck] = (unsigned short)(K - k0 < per ? K - k0 : per);
+                ck->cols[nck] = (unsigned short)C;
+            }
+            ++nck;
+        }
+        return start;
+    };
+    auto blk_k = [&](int b) { return net.blk[b].type == MDQ_BLOCK_SAGE ? 2 * W : W; };
+    for (int b = 1; b < nb; ++b) L.ck_blk[b] = add_layer(net.blk[b].w_off, blk_k(b), W);
+    for (int i = 0; i < 3; ++i) L.ck_lin[i] = add_layer(net.lin_off[i], net.lin_in[i], net.lin_out[i]);
+    if (bwd) {
+        for (int i = 2; i >= 0; --i) L.ck_blin[i] = add_layer(net.lin_off[i], net.lin_in[i], net.lin_out[i]);
+        for (int b = nb - 1; b >= 1; --b) L.ck_bblk[b] = add_layer(net.blk[b].w_off, blk_k(b), W);
+    }
+    if (overflow) return MDQ_ESMEM;
+    L.nchunks = nck;
     return MDQ_OK;
 }
 
@@ -192,12 +246,31 @@ __device__ __forceinline__ float warp_sum(float v)
 __device__ __forceinline__ int topk_count_dev(float ratio, int n) { return __float2int_ru(__fmul_rn(ratio, (float)n)); }
 
 // Stable CSR by destination: rowptr[n+1], csr[E] = source of each in-edge, in edge_index order per row.
+// E <= 2*NT: every edge counts the earlier edges with its destination (its slot inside the row) in parallel;
+// larger graphs fall back to one warp walking the edge list with match_any.
 __device__ void build_csr(int n, int E, const int *es, const int *ed, int *rowptr, int *cursor, int *csr)
 {
     const int tid = threadIdx.x;
     for (int i = tid; i <= n; i += NT) cursor[i] = 0;
     __syncthreads();
-    for (int e = tid; e < E; e += NT) atomicAdd(&cursor[ed[e]], 1);
+    const bool par = E <= 2 * NT;
+    int myrank[2] = {0, 0};
+    if (par) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int e = tid + it * NT;
+            if (e < E) {
+                const int d = ed[e];
+                int r = 0;
+#pragma unroll 4
+                for (int e2 = 0; e2 < e; ++e2) r += (ed[e2] == d);
+                myrank[it] = r;
+                atomicAdd(&cursor[d], 1);
+            }
+        }
+    } else {
+        for (int e = tid; e < E; e += NT) atomicAdd(&cursor[ed[e]], 1);
+    }
     __syncthreads();
     if (tid < 32) {
         int carry = 0;
@@ -214,23 +287,33 @@ __device__ void build_csr(int n, int E, const int *es, const int *ed, int *rowpt
             carry += __shfl_sync(FULL, incl, 31);
         }
         if (tid == 0) rowptr[n] = carry;
-        __syncwarp();
-        for (int i = tid; i < n; i += 32) cursor[i] = rowptr[i];
-        __syncwarp();
-        for (int base = 0; base < E; base += 32) {
-            const int e = base + tid;
-            const bool valid = e < E;
-            const int d = valid ? ed[e] : (-1 - tid);
-            const unsigned m = __match_any_sync(FULL, d);
-            const int rank = __popc(m & ((1u << tid) - 1u));
-            const int pos = valid ? cursor[d] + rank : 0;
+        if (!par) {
             __syncwarp();
-            if (valid && (31 - __clz(m)) == tid) cursor[d] += __popc(m);
+            for (int i = tid; i < n; i += 32) cursor[i] = rowptr[i];
             __syncwarp();
-            if (valid) csr[pos] = es[e];
+            for (int base = 0; base < E; base += 32) {
+                const int e = base + tid;
+                const bool valid = e < E;
+                const int d = valid ? ed[e] : (-1 - tid);
+                const unsigned m = __match_any_sync(FULL, d);
+                const int rank = __popc(m & ((1u << tid) - 1u));
+                const int pos = valid ? cursor[d] + rank : 0;
+                __syncwarp();
+                if (valid && (31 - __clz(m)) == tid) cursor[d] += __popc(m);
+                __syncwarp();
+                if (valid) csr[pos] = es[e];
+            }
         }
     }
     __syncthreads();
+    if (par) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int e = tid + it * NT;
+            if (e < E) csr[rowptr[ed[e]] + myrank[it]] = es[e];
+        }
+        __syncthreads();
+    }
 }
 
 // out[r][c] = act(bias[c] + sum_k A[r][k] * WT[k][c]); 4x4 register tile, k ascending.
@@ -284,51 +367,205 @@ __device__ void dense_rows(int n, int K, const float *A, int lda, const float *W
     }
 }
 
-// rows x K times WT[K][O] (+ bias), split-K over MLP_SPLIT slices combined in slice order.
-__device__ void mlp_layer(int rows, int K, int O, const float *in, int ldi, const float *__restrict__ WT,
-                          const float *__restrict__ b, float *out, int ldo, bool relu, float *part)
+// ---- weight stream: cp.async (LDGSTS, 16 B per thread) global -> shared, ns-1 chunks in flight ----
+// (A single-thread cp.async.bulk / TMA version measured ~12 B/clk per SM here -- latency-bound on its few
+// outstanding requests -- so every thread issues its own 16-byte asynchronous copies instead.)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct WStream {
+    const float *params;
+    float *smem;
+    const int *o_stage;
+    const WChunks *ck;
+    int ns, nchunks;
+    long long *ftrace;  // optional fine trace (CTA 0, thread 0): 3 stamps per chunk from slot 128 on
+
+    __device__ __forceinline__ void stamp(int j, int which) const
+    {
+        if (ftrace && blockIdx.x == 0 && threadIdx.x == 0 && j < 100) ftrace[128 + 3 * j + which] = clock64();
+    }
+    __device__ __forceinline__ int rows(int j) const { return ck->rows[j]; }
+    // every thread copies its 16-byte units of chunk j and commits one group (empty past the last chunk)
+    __device__ __forceinline__ void issue(int j) const
+    {
+        if (j < nchunks) {
+            const int units = (ck->rows[j] * ck->cols[j]) >> 2;
+            const float *src = params + ck->off[j];
+            float *dst = smem + o_stage[j % ns];
+            for (int i = threadIdx.x; i < units; i += NT) cp_async16(dst + 4 * i, src + 4 * i);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void start() const  // once the stage regions are free; all threads call
+    {
+        for (int j = 0; j < ns - 1; ++j) issue(j);
+    }
+    // chunk j is complete and visible to all threads on return; refills the stage chunk j-1 used
+    __device__ __forceinline__ const float *wait(int j) const
+    {
+        stamp(j, 0);
+        switch (ns) {
+            case 2: cp_async_wait<0>(); break;
+            case 3: cp_async_wait<1>(); break;
+            case 4: cp_async_wait<2>(); break;
+            case 5: cp_async_wait<3>(); break;
+            case 6: cp_async_wait<4>(); break;
+            case 7: cp_async_wait<5>(); break;
+            default: cp_async_wait<6>(); break;
+        }
+        __syncthreads();
+        issue(j + ns - 1);
+        stamp(j, 1);
+        return smem + o_stage[j % ns];
+    }
+    __device__ __forceinline__ void release(int j) const { stamp(j, 2); }
+};
+
+// out[r][c] = act(bias[c] + sum_k A[r][k] * WT[k][c]) with WT streamed through shared-memory stages.
+// One 4x4 output tile per thread (host guarantees ceil(n/4) * W/4 <= NT); k ascending.
+__device__ void dense_stream(const WStream &ws, int j0, int n, int K, const float *A, int lda, const float *bias, float *out,
+                             int ldo, int W, bool relu)
+{
+    const int q = W >> 2;
+    const int ngroups = (n + 3) >> 2;
+    const int item = threadIdx.x;
+    const bool active = item < ngroups * q;
+    const int rg = active ? item / q : 0;
+    const int c4 = active ? (item - rg * q) << 2 : 0;
+    const int r0 = rg << 2;
+    const float *a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
+    float acc[4][4];
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && active) b4 = __ldg(reinterpret_cast<const float4 *>(bias + c4));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+    int k = 0;
+    for (int jc = j0; k < K; ++jc) {
+        const float *st = ws.wait(jc);
+        const int rows = ws.rows(jc);
+        if (active) {
+#pragma unroll 2
+            for (int kk = 0; kk < rows; kk += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) w[t] = *reinterpret_cast<const float4 *>(st + (size_t)(kk + t) * W + c4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(a[j] + k + kk);
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        acc[j][0] = fmaf(xs[t], w[t].x, acc[j][0]);
+                        acc[j][1] = fmaf(xs[t], w[t].y, acc[j][1]);
+                        acc[j][2] = fmaf(xs[t], w[t].z, acc[j][2]);
+                        acc[j][3] = fmaf(xs[t], w[t].w, acc[j][3]);
+                    }
+                }
+            }
+        }
+        k += rows;
+        ws.release(jc);
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (r0 + j < n) {
+                float4 o4 = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+                *reinterpret_cast<float4 *>(out + (size_t)(r0 + j) * ldo + c4) = o4;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// rows x K times WT[K][O] (+ bias): every chunk is split over SL k-slices, partial sums combined in slice order.
+__device__ void mlp_stream(const WStream &ws, int j0, int rows, int K, int O, const float *in, int ldi,
+                           const float *__restrict__ b, float *out, int ldo, bool relu, float *part)
 {
     const int RO = rows * O;
-    const int Ks = K / MLP_SPLIT;
-    for (int item = threadIdx.x; item < MLP_SPLIT * RO; item += NT) {
-        const int s = item / RO;
-        const int rem = item - s * RO;
-        const int r = rem / O, c = rem - r * O;
-        const float *xi = in + r * ldi + s * Ks;
-        const float *wp = WT + (size_t)(s * Ks) * O + c;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < Ks; ++k) acc = fmaf(xi[k], __ldg(wp + (size_t)k * O), acc);
-        part[item] = acc;
+    const int fit = NT / RO;
+    const int SL = fit >= 4 ? 4 : (fit >= 2 ? 2 : 1);
+    const int total = SL * RO;  // host guarantees total <= 2 * NT
+    float acc[2] = {0.f, 0.f};
+    int s_[2], r_[2], c_[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int item = threadIdx.x + it * NT;
+        const int ii = item < total ? item : 0;
+        s_[it] = ii / RO;
+        const int rem = ii - s_[it] * RO;
+        r_[it] = rem / O;
+        c_[it] = rem - r_[it] * O;
     }
+    int k = 0;
+    for (int jc = j0; k < K; ++jc) {
+        const float *st = ws.wait(jc);
+        const int cr = ws.rows(jc);
+        const int per = cr / SL;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            if (threadIdx.x + it * NT < total) {
+                const float *xi = in + r_[it] * ldi + k + s_[it] * per;
+                const float *wp = st + (size_t)(s_[it] * per) * O + c_[it];
+                float av = acc[it];
+#pragma unroll 4
+                for (int kk = 0; kk < per; ++kk) av = fmaf(xi[kk], wp[(size_t)kk * O], av);
+                acc[it] = av;
+            }
+        }
+        k += cr;
+        ws.release(jc);
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+        if (threadIdx.x + it * NT < total) part[threadIdx.x + it * NT] = acc[it];
     __syncthreads();
     for (int idx = threadIdx.x; idx < RO; idx += NT) {
         const int r = idx / O, c = idx - r * O;
         float v = __ldg(b + c);
-#pragma unroll
-        for (int s = 0; s < MLP_SPLIT; ++s) v += part[s * RO + idx];
+        for (int sidx = 0; sidx < SL; ++sidx) v += part[sidx * RO + idx];
         out[r * ldo + c] = relu ? fmaxf(v, 0.f) : v;
     }
     __syncthreads();
 }
 
-// v[k] = sum_c d[c] * WT[k][c]  (one warp per k, lanes over c; used for input gradients)
-__device__ void matvec_t(int K, int C, const float *d, const float *__restrict__ WT, float *v, const float *gate)
+// out[r][k] = gate(k) * sum_c D[r][c] * WT[k][c]: input gradients; one warp per (r, k), lanes over c.
+__device__ void matmul_t_stream(const WStream &ws, int j0, int K, int C, int nr, const float *D, int ldd, float *out, int ldo,
+                                const float *gate)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = warp; k < K; k += NWARP) {
-        float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(d[c], __ldg(WT + (size_t)k * C + c), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) v[k] = (gate == nullptr || gate[k] > 0.f) ? acc : 0.f;
+    int k = 0;
+    for (int jc = j0; k < K; ++jc) {
+        const float *st = ws.wait(jc);
+        const int rows = ws.rows(jc);
+        for (int t = warp; t < nr * rows; t += NWARP) {
+            const int r = t / rows, kk = t - r * rows;
+            float acc = 0.f;
+            for (int c = lane; c < C; c += 32) acc = fmaf(D[r * ldd + c], st[(size_t)kk * C + c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) out[r * ldo + k + kk] = (gate == nullptr || gate[k + kk] > 0.f) ? acc : 0.f;
+        }
+        k += rows;
+        ws.release(jc);
     }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
+__global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QArgs a)
 {
     extern __shared__ __align__(16) float smem[];
     const QLay &L = a.L;
@@ -365,6 +602,13 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
     int *amaxs = BWD ? reinterpret_cast<int *>(smem + L.o_amax) : nullptr;
 
     const float *P = a.params;
+    int trace_n = 0;
+#define MDQ_TRACE()                                                                              \
+    do {                                                                                         \
+        if (a.trace && blockIdx.x == 0 && tid == 0 && trace_n < 120) a.trace[trace_n] = clock64(); \
+        ++trace_n;                                                                               \
+    } while (0)
+    MDQ_TRACE();  // 0: start
 
     // ---- stage conv1 weights (+bias row) in shared memory, zero padded to KC1 rows ----
     {
@@ -375,7 +619,10 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         if (tid <= G) seg[1 * (G + 1) + tid] = 0;
         if (tid <= nb) ecnt[tid] = 0;
     }
-    __syncthreads();
+    // (no barrier here: the first graph's loads below are followed by one)
+    WStream wst;
+    wst.params = P; wst.smem = smem; wst.o_stage = L.o_stage;
+    wst.ck = &a.ck; wst.ns = L.nstage; wst.nchunks = L.nchunks; wst.ftrace = a.trace;
 
     // pool weight norm helper: each warp recomputes it (W <= 256 -> <= 8 values per lane)
     auto pool_weights = [&](int b, float (&pw)[8], float &wnorm) {
@@ -455,34 +702,45 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
             }
         }
         __syncthreads();
+        MDQ_TRACE();  // L1: inputs loaded
         build_csr(n, E, e1s, e1d, rowptr, cursor, csr);
-        for (int idx = tid; idx < n * F; idx += NT) {  // mean aggregation, edge order per row
-            const int i = idx / F, f = idx - i * F;
+        MDQ_TRACE();  // L1: csr
+        for (int i = warp; i < n; i += NWARP) {  // mean aggregation, edge order per row; lanes over features
             const int s0 = rowptr[i], s1 = rowptr[i + 1];
-            float sum = 0.f;
-            for (int s = s0; s < s1; ++s) sum += cat1[csr[s] * KC1 + F + f];
-            const int cnt = s1 - s0;
-            cat1[i * KC1 + f] = sum / (float)(cnt > 0 ? cnt : 1);
+            const float inv_cnt = (float)(s1 - s0 > 0 ? s1 - s0 : 1);
+            for (int f = lane; f < F; f += 32) {
+                float sum = 0.f;
+                for (int s = s0; s < s1; ++s) sum += cat1[csr[s] * KC1 + F + f];
+                cat1[i * KC1 + f] = sum / inv_cnt;
+            }
         }
         __syncthreads();
+        MDQ_TRACE();  // L1: aggregated
         dense_rows<true>(n, KC1, cat1, KC1, w1s, w1s + KC1 * W, big, W, W, true);
         __syncthreads();
+        MDQ_TRACE();  // L1: dense
         compute_scores(0, n, big, 0);
         __syncthreads();
+        MDQ_TRACE();  // L1: scores
         const int k = topk_count_dev(net.ratio, n);
         const int obase = seg[1 * (G + 1) + gi];
-        for (int i = tid; i < n; i += NT) {
+        for (int i = warp; i < n; i += NWARP) {
             const float si = score[i];
             int r = 0;
-            for (int j = 0; j < n; ++j) {
+            for (int j = lane; j < n; j += 32) {
                 const float sj = score[j];
                 r += (sj > si) || (sj == si && j < i);
             }
-            newid[i] = (r < k) ? (obase + r) : -1;
-            if (r < k) parent[L.n_max + L.rowoff[1] + obase + r] = i;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+            if (lane == 0) {
+                newid[i] = (r < k) ? (obase + r) : -1;
+                if (r < k) parent[L.n_max + L.rowoff[1] + obase + r] = i;
+            }
         }
         if (tid == 0) seg[1 * (G + 1) + gi + 1] = obase + k;
         __syncthreads();
+        MDQ_TRACE();  // L1: ranked
         {
             float *xo = xbuf + (size_t)(L.rowoff[1] + obase) * W;
             const int *par = parent + L.n_max + L.rowoff[1] + obase;
@@ -493,6 +751,11 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
                 xo[idx] = h * score[i];
                 if (BWD) (smem + L.o_h1k)[(size_t)(obase + r) * W + c] = h;
             }
+            if (BWD)
+                for (int idx = tid; idx < k * KC1; idx += NT) {
+                    const int r = idx / KC1, j = idx - r * KC1;
+                    (smem + L.o_c1k)[(size_t)(obase + r) * KC1 + j] = cat1[par[r] * KC1 + j];
+                }
         }
         __syncthreads();
         for (int c = tid; c < W; c += NT) {  // readout: max / mean over the kept rows
@@ -510,7 +773,11 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         }
         if (nb > 1) filter_edges(E, e1s, e1d, 0, e2s + L.eoff[1], e2d + L.eoff[1], &ecnt[1]);
         __syncthreads();
+        MDQ_TRACE();  // L1: gathered, read out, edges filtered
     }
+
+    // block 0 is done: conv1's staged weights, cat1 and the tail of `big` become weight-stream stages
+    wst.start();
 
     // ================================ blocks >= 1: rows of all `ng` graphs together ================================
     for (int b = 1; b < nb; ++b) {
@@ -523,6 +790,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         const int *es = e2s + L.eoff[b], *ed = e2d + L.eoff[b];
         const int rbase = L.n_max + L.rowoff[b];
         build_csr(nrows, E, es, ed, rowptr, cursor, csr);
+        MDQ_TRACE();  // Bk: csr
         if (net.blk[b].type == MDQ_BLOCK_SAGE) {
             for (int idx = tid; idx < nrows * W; idx += NT) {
                 const int i = idx / W, f = idx - i * W;
@@ -534,14 +802,15 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
                 cat2[(size_t)i * 2 * W + W + f] = X[idx];
             }
             __syncthreads();
-            dense_rows<false>(nrows, 2 * W, cat2, 2 * W, P + net.blk[b].w_off, P + net.blk[b].b_off, H, W, W, true);
+            dense_stream(wst, L.ck_blk[b], nrows, 2 * W, cat2, 2 * W, P + net.blk[b].b_off, H, W, W, true);
         } else {
             for (int i = tid; i < nrows; i += NT) {
                 int deg = 1;
                 for (int s = rowptr[i]; s < rowptr[i + 1]; ++s) deg += (csr[s] != i);
                 dis[i] = __fdiv_rn(1.f, __fsqrt_rn((float)deg));
             }
-            dense_rows<false>(nrows, W, X, W, P + net.blk[b].w_off, nullptr, cat2, W, W, false);
+            __syncthreads();
+            dense_stream(wst, L.ck_blk[b], nrows, W, X, W, nullptr, cat2, W, W, false);
             __syncthreads();
             const float *bias = P + net.blk[b].b_off;
             for (int idx = tid; idx < nrows * W; idx += NT) {
@@ -558,6 +827,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
             }
         }
         __syncthreads();
+        MDQ_TRACE();  // Bk: conv done
         compute_scores(b, nrows, H, rbase);
         if (tid == 0) {
             int acc = 0;
@@ -612,6 +882,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         }
         if (b + 1 < nb) filter_edges(E, es, ed, rbase, e2s + L.eoff[b + 1], e2d + L.eoff[b + 1], &ecnt[b + 1]);
         __syncthreads();
+        MDQ_TRACE();  // Bk: pooled, read out, edges filtered
     }
 
     // ================================ MLP + softmax + argmax ================================
@@ -619,9 +890,10 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
     float *y1 = ybuf, *y2 = ybuf + G * YM, *y3 = ybuf + 2 * G * YM;
     if (a.emb)
         for (int idx = tid; idx < ng * 2 * W; idx += NT) a.emb[(size_t)g0 * 2 * W + idx] = racc[idx];
-    mlp_layer(ng, net.lin_in[0], net.lin_out[0], racc, 2 * W, P + net.lin_off[0], P + net.lin_boff[0], y1, YM, true, part);
-    mlp_layer(ng, net.lin_in[1], net.lin_out[1], y1, YM, P + net.lin_off[1], P + net.lin_boff[1], y2, YM, true, part);
-    mlp_layer(ng, net.lin_in[2], net.lin_out[2], y2, YM, P + net.lin_off[2], P + net.lin_boff[2], y3, YM, false, part);
+    mlp_stream(wst, L.ck_lin[0], ng, net.lin_in[0], net.lin_out[0], racc, 2 * W, P + net.lin_boff[0], y1, YM, true, part);
+    mlp_stream(wst, L.ck_lin[1], ng, net.lin_in[1], net.lin_out[1], y1, YM, P + net.lin_boff[1], y2, YM, true, part);
+    mlp_stream(wst, L.ck_lin[2], ng, net.lin_in[2], net.lin_out[2], y2, YM, P + net.lin_boff[2], y3, YM, false, part);
+    MDQ_TRACE();  // MLP done
     const int A = net.out_dim;
     for (int gi = warp; gi < ng; gi += NWARP) {
         float *y = y3 + gi * YM;
@@ -655,6 +927,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         }
         if (!BWD && a.amax_out && lane == 0) a.amax_out[g0 + gi] = bi;
     }
+    MDQ_TRACE();  // softmax / argmax done
     if (!BWD) return;
 
     // =====================================================================================
@@ -681,6 +954,21 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
             for (int k = tid; k < l.K; k += NT) ii[k] = (in && k < in_n) ? in[k] : 0.f;
         }
     };
+    // all rpg rows of a layer in one flattened pass: rows >= nvalid are zero-filled
+    auto emit_rows = [&](const WLayer &l, int nvalid, const float *D, int ldd, const float *IN, int ldin, int in_n) {
+        float *dd = ws + l.d_off + (size_t)g * l.rpg * l.C;
+        for (int idx = tid; idx < l.rpg * l.C; idx += NT) {
+            const int r = idx / l.C, c = idx - r * l.C;
+            dd[idx] = (r < nvalid) ? D[(size_t)r * ldd + c] : 0.f;
+        }
+        if (l.K > 0) {
+            float *ii = ws + l.i_off + (size_t)g * l.rpg * l.K;
+            for (int idx = tid; idx < l.rpg * l.K; idx += NT) {
+                const int r = idx / l.K, k = idx - r * l.K;
+                ii[idx] = (r < nvalid && k < in_n) ? IN[(size_t)r * ldin + k] : 0.f;
+            }
+        }
+    };
 
     // ---- MLP backward ----
     {
@@ -698,18 +986,17 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         }
         __syncthreads();
         emit_row(wd.l[2 * nb + 2], 0, d3, y2, net.lin_in[2]);
-        matvec_t(net.lin_in[2], net.lin_out[2], d3, P + net.lin_off[2], d2, y2);
-        __syncthreads();
+        matmul_t_stream(wst, L.ck_blin[2], net.lin_in[2], net.lin_out[2], 1, d3, 0, d2, 0, y2);
         emit_row(wd.l[2 * nb + 1], 0, d2, y1, net.lin_in[1]);
-        matvec_t(net.lin_in[1], net.lin_out[1], d2, P + net.lin_off[1], d1, y1);
-        __syncthreads();
+        matmul_t_stream(wst, L.ck_blin[1], net.lin_in[1], net.lin_out[1], 1, d2, 0, d1, 0, y1);
         emit_row(wd.l[2 * nb + 0], 0, d1, racc, net.lin_in[0]);
-        matvec_t(net.lin_in[0], net.lin_out[0], d1, P + net.lin_off[0], dr, nullptr);
-        __syncthreads();
+        matmul_t_stream(wst, L.ck_blin[0], net.lin_in[0], net.lin_out[0], 1, d1, 0, dr, 0, nullptr);
     }
 
+    MDQ_TRACE();  // backward: MLP done
     // ---- conv blocks, last to first ----
     for (int b = nb - 1; b >= 0; --b) {
+        MDQ_TRACE();  // backward: block b starts
         const int n_b = (b == 0) ? (a.nptr[g + 1] - a.nptr[g]) : seg[b * (G + 1) + 1];
         const int k = seg[(b + 1) * (G + 1) + 1];  // kept rows (G == 1)
         // hidden rows of block b: block 0 keeps only its kept rows (compact, row r); blocks >= 1 keep all rows
@@ -768,8 +1055,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
         }
         __syncthreads();
         if (b == 0) {
-            for (int r = 0; r < lw.rpg; ++r)
-                emit_row(lw, r, r < k ? dp + r * W : nullptr, r < k ? cat1 + par[r] * KC1 : nullptr, 2 * F);
+            emit_rows(lw, k, dp, W, smem + L.o_c1k, KC1, 2 * F);
             break;
         }
         const float *X = xbuf + (size_t)L.rowoff[b] * W;
@@ -789,18 +1075,9 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
                 cat2[(size_t)r * 2 * W + W + f] = X[(size_t)i * W + f];
             }
             __syncthreads();
-            for (int r = 0; r < lw.rpg; ++r)
-                emit_row(lw, r, r < k ? dp + r * W : nullptr, r < k ? cat2 + (size_t)r * 2 * W : nullptr, 2 * W);
+            emit_rows(lw, k, dp, W, cat2, 2 * W, 2 * W);
             // dcat[r][kk] = sum_c dP[r][c] * WT[kk][c]
-            const float *WT = P + net.blk[b].w_off;
-            for (int t = warp; t < k * 2 * W; t += NWARP) {
-                const int r = t / (2 * W), kk = t - r * 2 * W;
-                float acc = 0.f;
-                for (int c = lane; c < W; c += 32) acc = fmaf(dp[r * W + c], __ldg(WT + (size_t)kk * W + c), acc);
-                acc = warp_sum(acc);
-                if (lane == 0) dcat[t] = acc;
-            }
-            __syncthreads();
+            matmul_t_stream(wst, L.ck_bblk[b], 2 * W, W, k, dp, W, dcat, 2 * W, nullptr);
             for (int idx = tid; idx < n_b * W; idx += NT) {
                 const int j = idx / W, f = idx - j * W;
                 float acc = 0.f;
@@ -844,19 +1121,14 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const QArgs a)
                 dcat[idx] = acc;
             }
             __syncthreads();
-            for (int r = 0; r < lw.rpg; ++r)
-                emit_row(lw, r, r < n_b ? dcat + (size_t)r * W : nullptr, r < n_b ? X + (size_t)r * W : nullptr, W);
-            const float *WT = P + net.blk[b].w_off;
-            for (int t = warp; t < n_b * W; t += NWARP) {
-                const int j = t / W, kk = t - j * W;
-                float acc = 0.f;
-                for (int c = lane; c < W; c += 32) acc = fmaf(dcat[(size_t)j * W + c], __ldg(WT + (size_t)kk * W + c), acc);
-                acc = warp_sum(acc);
-                if (lane == 0) dxb[t] = acc;
-            }
+            emit_rows(lw, n_b, dcat, W, X, W, W);
+            __syncthreads();
+            matmul_t_stream(wst, L.ck_bblk[b], W, W, n_b, dcat, W, dxb, W, nullptr);
         }
         __syncthreads();
     }
+    MDQ_TRACE();  // backward done
+#undef MDQ_TRACE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1004,9 +1276,14 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     }
 }
 
-int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, void (*kern)(const QArgs))
+int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck, void (*kern)(const QArgs))
 {
-    int rc = build_layout(*net, max_n, max_e, G, bwd, L);
+    int rc = build_layout(*net, max_n, max_e, G, bwd, L, ck);
+    if (rc == MDQ_ESMEM) {
+        mdq::set_error("qnet: graphs of %d nodes / %d edges do not fit the fused kernel's shared memory tiles "
+                       "(%d graph(s)/CTA); a layered large-graph path is not built yet", max_n, max_e, G);
+        return rc;
+    }
     if (rc != MDQ_OK) { mdq::set_error("qnet: unsupported network/size (rc=%d)", rc); return rc; }
     const size_t bytes = (size_t)L.total * 4;
     if (bytes > 227 * 1024) {
@@ -1019,12 +1296,16 @@ int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLa
     return MDQ_OK;
 }
 
+long long *g_trace = nullptr;
+
 }  // namespace
 
 // ================================================================================================
 // C ABI
 // ================================================================================================
 extern "C" {
+
+void mdq_qnet_set_trace(int64_t *device_buf) { g_trace = reinterpret_cast<long long *>(device_buf); }
 
 int64_t mdq_qnet_smem_bytes(const mdq_net_t *net, int max_n, int max_e, int gpc, int backward)
 {
@@ -1058,11 +1339,11 @@ int mdq_qnet_forward(const mdq_net_t *net, const float *params, const float *x, 
     const int G = mdq_qnet_pick_gpc(net, n_graphs, max_n, max_e);
     QArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = setup_launch(net, max_n, max_e, G, 0, a.L, qnet_kernel<false>);
+    int rc = setup_launch(net, max_n, max_e, G, 0, a.L, &a.ck, qnet_kernel<false>);
     if (rc != MDQ_OK) return rc;
     a.net = *net;
     a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
-    a.B = n_graphs; a.out = out; a.emb = embedding; a.amax_out = argmax;
+    a.B = n_graphs; a.out = out; a.emb = embedding; a.amax_out = argmax; a.trace = g_trace;
     const int grid = (n_graphs + G - 1) / G;
     qnet_kernel<false><<<grid, NT, (size_t)a.L.total * 4, (cudaStream_t)stream>>>(a);
     return mdq::check_launch("qnet_kernel<fwd>");
@@ -1098,12 +1379,12 @@ int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x,
     cudaStream_t st = (cudaStream_t)stream;
     QArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = setup_launch(net, max_n, max_e, 1, 1, a.L, qnet_kernel<true>);
+    int rc = setup_launch(net, max_n, max_e, 1, 1, a.L, &a.ck, qnet_kernel<true>);
     if (rc != MDQ_OK) return rc;
     build_wdesc(*net, n_graphs, max_n, a.wd);
     a.net = *net;
     a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
-    a.B = n_graphs; a.gout = grad_out; a.ws = workspace;
+    a.B = n_graphs; a.gout = grad_out; a.ws = workspace; a.trace = g_trace;
 
     const WDesc &wd = a.wd;
     int max_tasks = 1;

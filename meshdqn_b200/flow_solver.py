@@ -106,12 +106,12 @@ class DeviceMesh:
 
     def smooth(self, iters=50):
         """``Mesh.smooth(iters)`` (flow_solver.py:67,237) in exact Gauss-Seidel vertex order."""
-        level = torch.empty(self.nv, dtype=torch.int32, device=self.device)
+        self.smooth_status = torch.zeros(1, dtype=torch.int32, device=self.device)
         L = _lib.lib()
         p = _lib.ptr
         with torch.cuda.device(self.device):
-            rc = L.mdq_mesh_smooth(p(self.coords), self.nv, p(self.nbr_ptr), p(self.nbr_idx), p(self.vc_ptr), p(self.vc_idx),
-                                   p(self.cells), p(self.on_boundary), int(iters), p(level), _lib.stream_ptr())
+            rc = L.mdq_mesh_smooth(p(self.coords), self.nv, self.nc, p(self.nbr_ptr), p(self.nbr_idx), p(self.vc_ptr), p(self.vc_idx),
+                                   p(self.cells), p(self.on_boundary), int(iters), p(self.smooth_status), _lib.stream_ptr())
         _lib.check(rc, "mdq_mesh_smooth")
         self._host.pop("coords", None)
 

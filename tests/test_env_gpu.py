@@ -103,6 +103,7 @@ def test_greedy_episode_matches_oracle_and_golden(cuda_device, short):
 def test_do_nothing_action_and_attributes(cuda_device):
     env, renv = make_envs("ys930", cuda_device)
     n = env.action_space.n
+    env.get_state()
     assert n == 180 and env.N_CLOSEST == 180 and len(env.coord_map) == 180
     s, r, done, info = env.step(n)          # do nothing: window shifts by one (quirk B5), reward recomputed
     rs, rr, rdone, _ = renv.step(n)

@@ -137,6 +137,6 @@ def test_huber_kernel_matches_torch(cuda_device):
                                 0.9, select, _lib.ptr(loss), _lib.ptr(gq) if select else None, None if select else _lib.ptr(gq),
                                 _lib.stream_ptr())
         _lib.check(rc, "mdq_huber_replay")
-        assert abs(float(loss) - float(loss_ref)) < 1e-6
+        assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
         gref = a1.grad if select else a2.grad
-        assert (gq.cpu() - gref).abs().max() < 1e-7
+        assert (gq.cpu() - gref).abs().max() < 1e-6
