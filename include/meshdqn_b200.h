@@ -99,6 +99,19 @@ int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x,
                       const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
                       int max_n, int max_e, const float *grad_out, float *grad, float *workspace, void *stream);
 
+/* Fused replay gradient (airfoil_dqn.py:240-310): the backward kernel evaluates the Huber term itself from its
+ * recomputed forward, so the selected net's forward is never launched separately.
+ *   mode 1 (select): the batch is the B states; index = next_slot [B]; q_other = Q2(s') [n_next, A] (may be NULL
+ *                    when every transition is terminal); scalar [B] receives pred_b = Q1(s_b)[a_b].
+ *   mode 2         : the batch is the n_next next-states; index = owner [n_next] (transition of each row);
+ *                    q_other = Q1(s) [B, A]; scalar [n_next] receives max_a Q2(s'_g).
+ * next_slot [B] is needed in both modes for the loss; loss = mean Huber over `batch` transitions; grad [n_params]. */
+int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                             const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                             int max_n, int max_e, int mode, const int32_t *action, const float *reward,
+                             const int32_t *index, const int32_t *next_slot, const float *q_other, int batch, float gamma,
+                             float *scalar, float *loss, float *grad, float *workspace, void *stream);
+
 /* Replay-minibatch loss (replaces /root/reference/airfoil_dqn.py:264,267-283,303-304):
  *   pred_b = q1[b, action[b]];  target_b = reward[b] + gamma * (nonfinal[b] ? max_a q2[slot[b], a] : 0)
  *   loss = mean_b huber(pred_b - target_b, delta = 1)

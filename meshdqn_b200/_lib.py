@@ -87,6 +87,8 @@ _SIGS = {
     "mdq_qnet_forward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mdq_qnet_bwd_workspace_floats": (c_int64, [POINTER(mdq_net_t), c_int, c_int]),
     "mdq_qnet_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "mdq_qnet_replay_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                                         _P, c_int, c_float, _P, _P, _P, _P, _P]),
     "mdq_huber_replay": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P]),
     "mdq_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "mdq_scan_i32": (c_int, [_P, _P, c_int, _P]),

@@ -316,6 +316,27 @@ class _FusedQNet(nn.Module):
                                      max_e, _lib.ptr(gout), _lib.ptr(flat_grad), _lib.ptr(self._ws), _lib.stream_ptr())
         _lib.check(rc, "mdq_qnet_backward")
 
+    def _launch_replay_backward(self, x, ei, nptr, eptr, B, max_n, max_e, mode, action, reward, index, next_slot, q_other,
+                                batch, gamma, scalar, loss, flat_grad):
+        self._ensure_packed()
+        net = self._net
+        net.x_stride = int(x.shape[1])
+        L = _lib.lib()
+        need = int(L.mdq_qnet_bwd_workspace_floats(net, B, max_n))
+        if need < 0:
+            raise RuntimeError("mdq_qnet_bwd_workspace_floats failed")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty(need, dtype=torch.float32, device=x.device)
+        E = int(ei.shape[1])
+        with torch.cuda.device(x.device):
+            rc = L.mdq_qnet_replay_backward(net, _lib.ptr(self._flat), _lib.ptr(x), _lib.c_void_p(ei.data_ptr()),
+                                            _lib.c_void_p(ei.data_ptr() + 8 * E), _lib.ptr(nptr), _lib.ptr(eptr), B, max_n,
+                                            max_e, int(mode), _lib.ptr(action), _lib.ptr(reward), _lib.ptr(index),
+                                            _lib.ptr(next_slot), _lib.ptr(q_other), int(batch), float(gamma),
+                                            _lib.ptr(scalar), _lib.ptr(loss), _lib.ptr(flat_grad), _lib.ptr(self._ws),
+                                            _lib.stream_ptr())
+        _lib.check(rc, "mdq_qnet_replay_backward")
+
     def _forward_impl(self, data, embedding=False):
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
         self._ensure_packed()

@@ -73,6 +73,14 @@ struct QArgs {
     float *ws;
     WDesc wd;
     WChunks ck;
+    // fused replay gradient (rp_mode 0: grad_out given; 1: Huber through this net's Q(s)[a]; 2: through max_a Q(s'))
+    int rp_mode;
+    const int *rp_action;    // [B]   action of transition b
+    const float *rp_reward;  // [B]
+    const int *rp_index;     // mode 1: next_slot [B] (row of rp_qother or -1); mode 2: owner [n_next] (transition of row g)
+    const float *rp_qother;  // mode 1: Q2(s') [n_next, A]; mode 2: Q1(s) [B, A]
+    float rp_gamma, rp_inv_batch;
+    float *rp_scalar;        // [n_graphs] out: mode 1 pred_b, mode 2 max_a Q(s'_g)
     long long *trace;  // optional: clock64() of CTA 0 / thread 0 at phase boundaries (profiling aid)
 };
 
@@ -972,8 +980,8 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
 
     // ---- MLP backward ----
     {
-        const float *go = a.gout + (size_t)g * A;
-        if (warp == 0) {
+        if (warp == 0 && a.rp_mode == 0) {
+            const float *go = a.gout + (size_t)g * A;
             float dot = 0.f;
             if (net.softmax) {
                 for (int c = lane; c < A; c += 32) dot = fmaf(__ldg(go + c), y3[c], dot);
@@ -981,6 +989,53 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
             }
             for (int c = lane; c < A; c += 32) {
                 const float gc = __ldg(go + c);
+                d3[c] = net.softmax ? y3[c] * (gc - dot) : gc;
+            }
+        } else if (warp == 0) {
+            // Huber(delta=1, mean) on pred = Q1(s)[a] vs target = r + gamma * max_a Q2(s'), airfoil_dqn.py:264-304,
+            // evaluated here so the selected net's forward is not launched twice
+            int sel;
+            float pred, nsv, rew;
+            if (a.rp_mode == 1) {
+                sel = a.rp_action[g];
+                pred = y3[sel];
+                rew = a.rp_reward[g];
+                const int slot = a.rp_index[g];
+                float m = -INFINITY;
+                if (slot >= 0) {
+                    const float *q = a.rp_qother + (size_t)slot * A;
+                    for (int c = lane; c < A; c += 32) m = fmaxf(m, __ldg(q + c));
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+                }
+                nsv = slot >= 0 ? m : 0.f;
+                if (lane == 0) a.rp_scalar[g] = pred;
+            } else {
+                const int b = a.rp_index[g];
+                pred = __ldg(a.rp_qother + (size_t)b * A + a.rp_action[b]);
+                rew = a.rp_reward[b];
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < A; c += 32) {
+                    const float v = y3[c];
+                    if (v > bv) { bv = v; bi = c; }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const float ov = __shfl_xor_sync(FULL, bv, o);
+                    const int oi = __shfl_xor_sync(FULL, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                sel = bi;
+                nsv = bv;
+                if (lane == 0) a.rp_scalar[g] = bv;
+            }
+            const float d = pred - (nsv * a.rp_gamma + rew);
+            const float hd = (fabsf(d) < 1.f) ? d : (d > 0.f ? 1.f : -1.f);
+            const float gsel = (a.rp_mode == 1) ? hd * a.rp_inv_batch : -hd * a.rp_gamma * a.rp_inv_batch;
+            const float dot = net.softmax ? gsel * y3[sel] : 0.f;
+            for (int c = lane; c < A; c += 32) {
+                const float gc = (c == sel) ? gsel : 0.f;
                 d3[c] = net.softmax ? y3[c] * (gc - dot) : gc;
             }
         }
@@ -1258,6 +1313,43 @@ __global__ void __launch_bounds__(256) huber_kernel(const float *__restrict__ q1
     if (tid == 0) *loss = red[0] / (float)B;
 }
 
+// loss = mean_b huber(pred_b - (r_b + gamma * nsv_b)) from the scalars the fused backward left behind
+__global__ void __launch_bounds__(256) replay_loss_kernel(int mode, const float *__restrict__ scalar,
+                                                          const float *__restrict__ qother, const int *__restrict__ action,
+                                                          const float *__restrict__ reward, const int *__restrict__ next_slot,
+                                                          int B, int A, float gamma, float *loss)
+{
+    __shared__ float red[256];
+    const int tid = threadIdx.x;
+    float lsum = 0.f;
+    for (int b = tid; b < B; b += 256) {
+        const int slot = next_slot[b];
+        float pred, nsv = 0.f;
+        if (mode == 1) {
+            pred = scalar[b];
+            if (slot >= 0) {
+                const float *q = qother + (size_t)slot * A;
+                float m = q[0];
+                for (int c = 1; c < A; ++c) m = fmaxf(m, q[c]);
+                nsv = m;
+            }
+        } else {
+            pred = qother[(size_t)b * A + action[b]];
+            if (slot >= 0) nsv = scalar[slot];
+        }
+        const float d = pred - (nsv * gamma + reward[b]);
+        const float ad = fabsf(d);
+        lsum += (ad < 1.f) ? 0.5f * d * d : (ad - 0.5f);
+    }
+    red[tid] = lsum;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) *loss = red[0] / (float)B;
+}
+
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                             float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
                             float gscale, float step_size, float bc2_sqrt)
@@ -1368,24 +1460,17 @@ int64_t mdq_qnet_bwd_workspace_floats(const mdq_net_t *net, int n_graphs, int ma
     return (int64_t)wd.total + partial + 64;
 }
 
-int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
-                      const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
-                      int max_n, int max_e, const float *grad_out, float *grad, float *workspace, void *stream)
+static int qnet_backward_launch(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                                const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                                int max_n, int max_e, QArgs &a, float *grad, float *workspace, void *stream)
 {
-    if (!net || !params || !x || !grad_out || !grad || !workspace || n_graphs < 1) {
-        mdq::set_error("mdq_qnet_backward: null argument or empty batch");
-        return MDQ_EINVAL;
-    }
     cudaStream_t st = (cudaStream_t)stream;
-    QArgs a;
-    memset(&a, 0, sizeof(a));
     int rc = setup_launch(net, max_n, max_e, 1, 1, a.L, &a.ck, qnet_kernel<true>);
     if (rc != MDQ_OK) return rc;
     build_wdesc(*net, n_graphs, max_n, a.wd);
     a.net = *net;
     a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
-    a.B = n_graphs; a.gout = grad_out; a.ws = workspace; a.trace = g_trace;
-
+    a.B = n_graphs; a.ws = workspace; a.trace = g_trace;
     const WDesc &wd = a.wd;
     int max_tasks = 1;
     for (int i = 0; i < wd.nl; ++i) {
@@ -1398,7 +1483,6 @@ int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x,
     float *d_partial = workspace + wd.total;
     cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net->n_params * sizeof(float), st);
     if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
-
     qnet_kernel<true><<<n_graphs, NT, (size_t)a.L.total * 4, st>>>(a);
     rc = mdq::check_launch("qnet_kernel<bwd>");
     if (rc != MDQ_OK) return rc;
@@ -1409,6 +1493,44 @@ int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x,
     dim3 rg(16, wd.nl);
     wgrad_reduce_kernel<<<rg, 256, 0, st>>>(a.wd, n_graphs, d_partial, grad);
     return mdq::check_launch("wgrad_reduce_kernel");
+}
+
+int mdq_qnet_backward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                      const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                      int max_n, int max_e, const float *grad_out, float *grad, float *workspace, void *stream)
+{
+    if (!net || !params || !x || !grad_out || !grad || !workspace || n_graphs < 1) {
+        mdq::set_error("mdq_qnet_backward: null argument or empty batch");
+        return MDQ_EINVAL;
+    }
+    QArgs a;
+    memset(&a, 0, sizeof(a));
+    a.gout = grad_out;
+    return qnet_backward_launch(net, params, x, edge_src, edge_dst, node_ptr, edge_ptr, n_graphs, max_n, max_e, a, grad,
+                                workspace, stream);
+}
+
+int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const float *x, const int64_t *edge_src,
+                             const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
+                             int max_n, int max_e, int mode, const int32_t *action, const float *reward,
+                             const int32_t *index, const int32_t *next_slot, const float *q_other, int batch, float gamma,
+                             float *scalar, float *loss, float *grad, float *workspace, void *stream)
+{
+    if (!net || !params || !x || !grad || !workspace || !action || !reward || !index || !next_slot || !scalar || !loss ||
+        n_graphs < 1 || batch < 1 || (mode != 1 && mode != 2) || (mode == 2 && !q_other)) {
+        mdq::set_error("mdq_qnet_replay_backward: bad argument");
+        return MDQ_EINVAL;
+    }
+    QArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rp_mode = mode; a.rp_action = action; a.rp_reward = reward; a.rp_index = index; a.rp_qother = q_other;
+    a.rp_gamma = gamma; a.rp_inv_batch = 1.f / (float)batch; a.rp_scalar = scalar;
+    int rc = qnet_backward_launch(net, params, x, edge_src, edge_dst, node_ptr, edge_ptr, n_graphs, max_n, max_e, a, grad,
+                                  workspace, stream);
+    if (rc != MDQ_OK) return rc;
+    replay_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mode, scalar, q_other, action, reward, next_slot, batch,
+                                                           net->out_dim, gamma, loss);
+    return mdq::check_launch("replay_loss_kernel");
 }
 
 int mdq_huber_replay(const float *q1, const float *q2, const int32_t *action, const float *reward,

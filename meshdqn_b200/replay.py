@@ -13,7 +13,8 @@ The reference routes this through Ray actors (replay actor -> worker -> paramete
 apply_gradients steps the optimizer before the gradients are set and re-creates the optimizer on
 every call, losing Adam's moments (:188-199).  Those are defects, not semantics (SURVEY.md App. B,
 "do not replicate"): here each net keeps one Adam state and the step is
-forward(Q1) -> forward(Q2) -> Huber -> backward(selected) -> [all-reduce] -> Adam, 7 launches.
+forward(other net) -> backward(selected net; recomputes its forward and evaluates the Huber term in
+place) -> weight-gradient reduce -> loss -> [all-reduce] -> Adam.
 
 Multi-GPU: graphs are independent, so each rank takes its own B transitions; the only exchange is
 ONE all-reduce (sum) of the flat fp32 gradient (the first ``n_used`` floats of the flat buffer,
@@ -34,9 +35,16 @@ class ReplayBatch:
     transition b's next state, -1 if terminal; ``actions`` i32 [B]; ``rewards`` f32 [B].
     """
 
-    def __init__(self, states, actions, next_states, next_slot, rewards):
+    def __init__(self, states, actions, next_states, next_slot, rewards, owner=None):
         self.states, self.actions, self.next_states, self.next_slot, self.rewards = \
             states, actions, next_states, next_slot, rewards
+        if owner is None:  # owner[g] = transition whose next state is row g of next_states (inverse of next_slot)
+            ns = next_slot.cpu()
+            idx = torch.nonzero(ns >= 0, as_tuple=False)[:, 0]
+            owner = torch.zeros(max(int(idx.numel()), 1), dtype=torch.int32)
+            owner[ns[idx].long()] = idx.to(torch.int32)
+            owner = owner.to(next_slot.device)
+        self.owner = owner
 
     @classmethod
     def from_transitions(cls, transitions):
@@ -58,13 +66,13 @@ class ReplayBatch:
     def pin_memory(self):
         return ReplayBatch(self.states.pin_memory(), self.actions.pin_memory(),
                            None if self.next_states is None else self.next_states.pin_memory(),
-                           self.next_slot.pin_memory(), self.rewards.pin_memory())
+                           self.next_slot.pin_memory(), self.rewards.pin_memory(), self.owner.pin_memory())
 
     def to(self, device, non_blocking=True):
         return ReplayBatch(self.states.to(device, non_blocking=non_blocking), self.actions.to(device, non_blocking=non_blocking),
                            None if self.next_states is None else self.next_states.to(device, non_blocking=non_blocking),
                            self.next_slot.to(device, non_blocking=non_blocking),
-                           self.rewards.to(device, non_blocking=non_blocking))
+                           self.rewards.to(device, non_blocking=non_blocking), self.owner.to(device, non_blocking=non_blocking))
 
     def h2d_bytes(self):
         n = 0
@@ -73,7 +81,7 @@ class ReplayBatch:
                 continue
             n += b.x.numel() * b.x.element_size() + b.edge_index.numel() * 8 + b.ptr.numel() * 8 + b.eptr.numel() * 8 + \
                 b.batch.numel() * 8
-        return n + self.actions.numel() * 4 + self.next_slot.numel() * 4 + self.rewards.numel() * 4
+        return n + self.actions.numel() * 4 + self.next_slot.numel() * 4 + self.rewards.numel() * 4 + self.owner.numel() * 4
 
 
 def multistep_lr(base_lr, step, milestones=(500000, 1000000, 1500000), gamma=0.1):
@@ -125,40 +133,62 @@ class ReplayTrainer:
 
     # -- one replay step ----------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, batch: ReplayBatch):
-        """Returns the Huber loss (device scalar tensor); parameters of the selected net are updated."""
+    def step(self, batch: ReplayBatch, fused: bool = True):
+        """Returns the Huber loss (device scalar tensor); parameters of the selected net are updated.
+
+        fused=True (default): forward of the NON-selected net only; the selected net's backward kernel
+        recomputes its own forward and evaluates the Huber term in place (mdq_qnet_replay_backward):
+        launches = forward + memset + backward + 2 weight-gradient + loss + Adam.
+        fused=False: the reference's literal sequence forward(Q1), forward(Q2), Huber, backward (used by tests).
+        """
         net1, net2 = self.nets
         dev = batch.states.x.device
         L = _lib.lib()
         p = _lib.ptr
         B = int(batch.actions.shape[0])
         s_args = net1._prep(batch.states)
-        with self._timed("qnet_fwd"):
-            q1, _, _ = net1._launch_forward(*s_args, False, False)
-        if batch.next_states is not None:
-            n_args = net2._prep(batch.next_states)
-            with self._timed("qnet_fwd"):
-                q2, _, _ = net2._launch_forward(*n_args, False, False)
-            n_next = int(q2.shape[0])
-        else:
-            n_args, q2, n_next = None, None, 0
-        A = int(q1.shape[1])
+        n_args = net2._prep(batch.next_states) if batch.next_states is not None else None
+        n_next = int(n_args[4]) if n_args is not None else 0
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         sel = 0 if self.select else 1
-        gq = torch.empty((B if self.select else max(n_next, 1), A), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev), self._timed("huber"):
-            rc = L.mdq_huber_replay(p(q1), p(q2), p(batch.actions), p(batch.rewards), p(batch.next_slot), B, n_next, A,
-                                    self.gamma, 1 if self.select else 0, p(loss), p(gq) if self.select else None,
-                                    None if self.select else p(gq), _lib.stream_ptr())
-        _lib.check(rc, "mdq_huber_replay")
         net = self.nets[sel]
         st = self._adam_state(sel)
-        if self.select or n_args is not None:
-            args = s_args if self.select else n_args
+        A = net._net.out_dim
+        if fused and (self.select or n_args is not None):
+            if self.select:
+                q_other = None
+                if n_args is not None:
+                    with self._timed("qnet_fwd"):
+                        q_other, _, _ = net2._launch_forward(*n_args, False, False)
+                args, mode, index = s_args, 1, batch.next_slot
+            else:
+                with self._timed("qnet_fwd"):
+                    q_other, _, _ = net1._launch_forward(*s_args, False, False)
+                args, mode = n_args, 2
+                index = batch.owner
+            scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
             with self._timed("qnet_bwd+wgrad"):
-                net._launch_backward(*args, gq, st["g"])
+                net._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, q_other, B,
+                                            self.gamma, scalar, loss, st["g"])
         else:
-            st["g"].zero_()
+            with self._timed("qnet_fwd"):
+                q1, _, _ = net1._launch_forward(*s_args, False, False)
+            q2 = None
+            if n_args is not None:
+                with self._timed("qnet_fwd"):
+                    q2, _, _ = net2._launch_forward(*n_args, False, False)
+            gq = torch.empty((B if self.select else max(n_next, 1), A), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev), self._timed("huber"):
+                rc = L.mdq_huber_replay(p(q1), p(q2), p(batch.actions), p(batch.rewards), p(batch.next_slot), B, n_next, A,
+                                        self.gamma, 1 if self.select else 0, p(loss), p(gq) if self.select else None,
+                                        None if self.select else p(gq), _lib.stream_ptr())
+            _lib.check(rc, "mdq_huber_replay")
+            if self.select or n_args is not None:
+                args = s_args if self.select else n_args
+                with self._timed("qnet_bwd+wgrad"):
+                    net._launch_backward(*args, gq, st["g"])
+            else:
+                st["g"].zero_()
         n_used = net._n_used
         if self.world > 1:
             with self._timed("allreduce"):

@@ -36,8 +36,9 @@ def build(dev, seed2=77):
     return nets, refs
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("select", [True, False])
-def test_replay_step_matches_oracle(cuda_device, select):
+def test_replay_step_matches_oracle(cuda_device, select, fused):
     from meshdqn_b200.replay import ReplayBatch, ReplayTrainer
     (n1, n2), (r1, r2) = build(cuda_device)
     g = torch.Generator().manual_seed(21)
@@ -50,7 +51,7 @@ def test_replay_step_matches_oracle(cuda_device, select):
     opt = torch.optim.Adam(tgt_ref.parameters(), lr=lr, weight_decay=wd)
     mask = rb.next_slot >= 0
     for it in range(3):
-        loss = trainer.step(rb.to(cuda_device))
+        loss = trainer.step(rb.to(cuda_device), fused=fused)
         opt.zero_grad()
         ref_loss = gnn_ref.replay_loss(r1, r2, rb.states, rb.actions.long(), (rb.next_states, mask), rb.rewards, gamma, select)
         ref_loss.backward()
@@ -129,11 +130,11 @@ def test_huber_kernel_matches_torch(cuda_device):
         nsv[:B2] = a2.max(1)[0][slot[:B2].long()]
         loss_ref = torch.nn.functional.huber_loss(a1[torch.arange(B), act.long()], nsv * 0.9 + rew)
         loss_ref.backward()
-        d = lambda t: t.to(cuda_device)
+        dq1, dq2, dact, drew, dslot = (t.to(cuda_device) for t in (q1, q2, act, rew, slot))  # keep the device copies alive
         loss = torch.empty(1, device=cuda_device)
         gq = torch.empty((B if select else B2, A), device=cuda_device)
         L = _lib.lib()
-        rc = L.mdq_huber_replay(_lib.ptr(d(q1)), _lib.ptr(d(q2)), _lib.ptr(d(act)), _lib.ptr(d(rew)), _lib.ptr(d(slot)), B, B2, A,
+        rc = L.mdq_huber_replay(_lib.ptr(dq1), _lib.ptr(dq2), _lib.ptr(dact), _lib.ptr(drew), _lib.ptr(dslot), B, B2, A,
                                 0.9, select, _lib.ptr(loss), _lib.ptr(gq) if select else None, None if select else _lib.ptr(gq),
                                 _lib.stream_ptr())
         _lib.check(rc, "mdq_huber_replay")
