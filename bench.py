@@ -118,6 +118,16 @@ def harvest_transitions(make_env, n, seed):
     return out[:n]
 
 
+def random_transitions(n, seed):
+    """Seeded random graphs of ys930 state size (180 x 17, ~372 edges): ONLY for short profiler runs
+    (--fast-setup); the benchmark proper harvests real transitions."""
+    from meshdqn_b200.data import Data
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda: Data(x=torch.randn(180, 17, generator=g), edge_index=torch.randint(0, 180, (2, 372), generator=g))
+    return [(mk(), int(torch.randint(0, 181, (1,), generator=g)), None if i % 16 == 15 else mk(), float(torch.rand(1, generator=g)))
+            for i in range(n)]
+
+
 def env_factory(device=None):
     from conftest import make_config, oracle_fields
     coords, cells, U, P = oracle_fields("ys930")
@@ -197,7 +207,7 @@ def run_ours(args):
     L = _lib.lib()
     K, W = args.steps, max(args.warmup, 3)
 
-    tr = harvest_transitions(env_factory(dev), BATCH, 1000 + rank)
+    tr = random_transitions(BATCH, 1000 + rank) if args.fast_setup else harvest_transitions(env_factory(dev), BATCH, 1000 + rank)
     rb_host = ReplayBatch.from_transitions(tr).pin_memory()
     rb_dev = rb_host.to(dev)
     torch.manual_seed(1370)
@@ -273,7 +283,8 @@ def run_ours(args):
             extras = measure_extras(dev, nets[0], rb_dev, flush, args)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world), "clocks": clk.summary(),
+                "config": dict(workload_config(world), **({"setup": "fast-setup: random graphs (profiling run, not a bench value)"} if args.fast_setup else {})),
+                "clocks": clk.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rb_host.h2d_bytes()), "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "qnet_kernel<bwd> + wgrad_partial + wgrad_reduce", "achieved": achieved,
@@ -396,6 +407,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--big", action="store_true", help="use the ~1M-triangle synthetic mesh for the re-interpolation extra")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--fast-setup", action="store_true", help="random graphs instead of harvested transitions (profiler runs only)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
