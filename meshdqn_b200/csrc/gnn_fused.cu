@@ -22,6 +22,7 @@ constexpr int NWARP = NT / 32;
 constexpr int MAXB = MDQ_MAX_BLOCKS;
 constexpr int MLP_SPLIT = 4;
 constexpr unsigned FULL = 0xffffffffu;
+using eid_t = unsigned short;  // CTA-local node/row id in shared memory
 constexpr int MAX_STAGE = 8;
 constexpr int STAGE_WORDS = 4096;  // 16 KB per stage
 constexpr int MAXCH = 128;
@@ -159,11 +160,13 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     L.o_mbar = take(2 * MAX_STAGE);
     L.o_xbuf = take(L.xrows * W);
     L.o_hbuf = take((bwd ? L.xrows : gcap1) * W);
-    L.o_e1s = take(L.e_max);
-    L.o_e1d = take(L.e_max);
-    L.o_csr = take(G * L.e_max);
-    L.o_e2s = take(L.e2cap);
-    L.o_e2d = take(L.e2cap);
+    // edge endpoints / CSR columns are CTA-local row ids < 65536: stored as 16-bit, two per word
+    if (max_n > 65535 || gcap1 > 65535) return MDQ_ESMEM;
+    L.o_e1s = take((L.e_max + 1) / 2);
+    L.o_e1d = take((L.e_max + 1) / 2);
+    L.o_csr = take((G * L.e_max + 1) / 2);
+    L.o_e2s = take((L.e2cap + 1) / 2);
+    L.o_e2d = take((L.e2cap + 1) / 2);
     const int rmax = max_n > gcap1 ? max_n : gcap1;
     L.o_rowptr = take(rmax + 2);
     L.o_cursor = take(rmax + 2);
@@ -256,7 +259,7 @@ __device__ __forceinline__ int topk_count_dev(float ratio, int n) { return __flo
 // Stable CSR by destination: rowptr[n+1], csr[E] = source of each in-edge, in edge_index order per row.
 // E <= 2*NT: every edge counts the earlier edges with its destination (its slot inside the row) in parallel;
 // larger graphs fall back to one warp walking the edge list with match_any.
-__device__ void build_csr(int n, int E, const int *es, const int *ed, int *rowptr, int *cursor, int *csr)
+__device__ void build_csr(int n, int E, const eid_t *es, const eid_t *ed, int *rowptr, int *cursor, eid_t *csr)
 {
     const int tid = threadIdx.x;
     for (int i = tid; i <= n; i += NT) cursor[i] = 0;
@@ -302,7 +305,7 @@ __device__ void build_csr(int n, int E, const int *es, const int *ed, int *rowpt
             for (int base = 0; base < E; base += 32) {
                 const int e = base + tid;
                 const bool valid = e < E;
-                const int d = valid ? ed[e] : (-1 - tid);
+                const int d = valid ? (int)ed[e] : (-1 - tid);
                 const unsigned m = __match_any_sync(FULL, d);
                 const int rank = __popc(m & ((1u << tid) - 1u));
                 const int pos = valid ? cursor[d] + rank : 0;
@@ -590,11 +593,11 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
     float *cat2 = smem + L.o_cat2;
     float *xbuf = smem + L.o_xbuf;
     float *hbuf = smem + L.o_hbuf;
-    int *e1s = reinterpret_cast<int *>(smem + L.o_e1s);
-    int *e1d = reinterpret_cast<int *>(smem + L.o_e1d);
-    int *csr = reinterpret_cast<int *>(smem + L.o_csr);
-    int *e2s = reinterpret_cast<int *>(smem + L.o_e2s);
-    int *e2d = reinterpret_cast<int *>(smem + L.o_e2d);
+    eid_t *e1s = reinterpret_cast<eid_t *>(smem + L.o_e1s);
+    eid_t *e1d = reinterpret_cast<eid_t *>(smem + L.o_e1d);
+    eid_t *csr = reinterpret_cast<eid_t *>(smem + L.o_csr);
+    eid_t *e2s = reinterpret_cast<eid_t *>(smem + L.o_e2s);
+    eid_t *e2d = reinterpret_cast<eid_t *>(smem + L.o_e2d);
     int *rowptr = reinterpret_cast<int *>(smem + L.o_rowptr);
     int *cursor = reinterpret_cast<int *>(smem + L.o_cursor);
     float *score = smem + L.o_score;
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
     };
 
     // ordered compaction of kept edges (both endpoints kept), ids mapped through newid (+base of the row arrays)
-    auto filter_edges = [&](int E, const int *es, const int *ed, int nbase, int *os, int *od, int *count) {
+    auto filter_edges = [&](int E, const eid_t *es, const eid_t *ed, int nbase, eid_t *os, eid_t *od, int *count) {
         if (warp == 0) {
             int cnt = *count;
             for (int base = 0; base < E; base += 32) {
@@ -678,8 +681,8 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
                 const unsigned m = __ballot_sync(FULL, keep);
                 if (keep) {
                     const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-                    os[pos] = s;
-                    od[pos] = d;
+                    os[pos] = (eid_t)s;
+                    od[pos] = (eid_t)d;
                 }
                 cnt += __popc(m);
             }
@@ -705,8 +708,8 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
                 cat1[i * KC1 + 2 * F + f] = 0.f;
             }
             for (int e = tid; e < E; e += NT) {
-                e1s[e] = (int)(a.esrc[eb0 + e] - nb0);
-                e1d[e] = (int)(a.edst[eb0 + e] - nb0);
+                e1s[e] = (eid_t)(a.esrc[eb0 + e] - nb0);
+                e1d[e] = (eid_t)(a.edst[eb0 + e] - nb0);
             }
         }
         __syncthreads();
@@ -795,7 +798,7 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
         const int E = ecnt[b];
         const float *X = xbuf + (size_t)L.rowoff[b] * W;
         float *H = hbuf + (size_t)L.hoff[b] * W;
-        const int *es = e2s + L.eoff[b], *ed = e2d + L.eoff[b];
+        const eid_t *es = e2s + L.eoff[b], *ed = e2d + L.eoff[b];
         const int rbase = L.n_max + L.rowoff[b];
         build_csr(nrows, E, es, ed, rowptr, cursor, csr);
         MDQ_TRACE();  // Bk: csr
@@ -1210,6 +1213,7 @@ __device__ __forceinline__ void wg_layer_geom(const WDesc &wd, int B, int li, in
 __global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int B, const float *__restrict__ ws,
                                                             float *__restrict__ partial)
 {
+    __shared__ __align__(16) float xin[WG_ROWS][WG_KG];  // the chunk's input rows, these WG_KG k-values (4 KB)
     const int li = blockIdx.y;
     const WLayer l = wd.l[li];
     if (l.rpg == 0) return;
@@ -1221,21 +1225,31 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int 
         const int rows = B * l.rpg;
         const int r0 = chunk * WG_ROWS, r1 = min(rows, r0 + WG_ROWS);
         const int k0 = kg * WG_KG;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < WG_ROWS * WG_KG; idx += blockDim.x) {
+            const int rr = idx / WG_KG, j = idx - rr * WG_KG;
+            const int r = r0 + rr, k = k0 + j;
+            float v = 0.f;
+            if (r < r1) v = (k < l.K) ? __ldg(ws + l.i_off + (size_t)r * l.K + k) : (k == l.K ? 1.f : 0.f);
+            xin[rr][j] = v;
+        }
+        __syncthreads();
         float *po = partial + poff + (size_t)t * WG_KG * l.C;
         for (int c = threadIdx.x; c < l.C; c += blockDim.x) {
             float acc[WG_KG];
 #pragma unroll
             for (int j = 0; j < WG_KG; ++j) acc[j] = 0.f;
             const float *dl = ws + l.d_off + c;
-            const float *in = ws + l.i_off;
-            for (int r = r0; r < r1; ++r) {
-                const float d = __ldg(dl + (size_t)r * l.C);
-#pragma unroll
-                for (int j = 0; j < WG_KG; ++j) {
-                    const int k = k0 + j;
-                    const float xv = (k < l.K) ? __ldg(in + (size_t)r * l.K + k) : (k == l.K ? 1.f : 0.f);
-                    acc[j] = fmaf(xv, d, acc[j]);
-                }
+            const int nr = r1 - r0;
+#pragma unroll 4
+            for (int rr = 0; rr < nr; ++rr) {
+                const float d = __ldg(dl + (size_t)(r0 + rr) * l.C);
+                const float4 xa = *reinterpret_cast<const float4 *>(&xin[rr][0]);
+                const float4 xb = *reinterpret_cast<const float4 *>(&xin[rr][4]);
+                acc[0] = fmaf(xa.x, d, acc[0]); acc[1] = fmaf(xa.y, d, acc[1]);
+                acc[2] = fmaf(xa.z, d, acc[2]); acc[3] = fmaf(xa.w, d, acc[3]);
+                acc[4] = fmaf(xb.x, d, acc[4]); acc[5] = fmaf(xb.y, d, acc[5]);
+                acc[6] = fmaf(xb.z, d, acc[6]); acc[7] = fmaf(xb.w, d, acc[7]);
             }
 #pragma unroll
             for (int j = 0; j < WG_KG; ++j)
@@ -1313,24 +1327,27 @@ __global__ void __launch_bounds__(256) huber_kernel(const float *__restrict__ q1
     if (tid == 0) *loss = red[0] / (float)B;
 }
 
-// loss = mean_b huber(pred_b - (r_b + gamma * nsv_b)) from the scalars the fused backward left behind
-__global__ void __launch_bounds__(256) replay_loss_kernel(int mode, const float *__restrict__ scalar,
-                                                          const float *__restrict__ qother, const int *__restrict__ action,
-                                                          const float *__restrict__ reward, const int *__restrict__ next_slot,
-                                                          int B, int A, float gamma, float *loss)
+// loss = mean_b huber(pred_b - (r_b + gamma * nsv_b)) from the scalars the fused backward left behind;
+// one warp per transition (max over A by lanes), fixed-shape reduction -> deterministic
+__global__ void __launch_bounds__(1024) replay_loss_kernel(int mode, const float *__restrict__ scalar,
+                                                           const float *__restrict__ qother, const int *__restrict__ action,
+                                                           const float *__restrict__ reward, const int *__restrict__ next_slot,
+                                                           int B, int A, float gamma, float *loss)
 {
-    __shared__ float red[256];
-    const int tid = threadIdx.x;
-    float lsum = 0.f;
-    for (int b = tid; b < B; b += 256) {
+    __shared__ float red[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float lsum = 0.f;  // meaningful in lane 0
+    for (int b = warp; b < B; b += 32) {
         const int slot = next_slot[b];
         float pred, nsv = 0.f;
         if (mode == 1) {
             pred = scalar[b];
             if (slot >= 0) {
                 const float *q = qother + (size_t)slot * A;
-                float m = q[0];
-                for (int c = 1; c < A; ++c) m = fmaxf(m, q[c]);
+                float m = -INFINITY;
+                for (int c = lane; c < A; c += 32) m = fmaxf(m, q[c]);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
                 nsv = m;
             }
         } else {
@@ -1341,13 +1358,14 @@ __global__ void __launch_bounds__(256) replay_loss_kernel(int mode, const float 
         const float ad = fabsf(d);
         lsum += (ad < 1.f) ? 0.5f * d * d : (ad - 0.5f);
     }
-    red[tid] = lsum;
+    if (lane == 0) red[warp] = lsum;
     __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-        if (tid < o) red[tid] += red[tid + o];
-        __syncthreads();
+    if (warp == 0) {
+        float v = red[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0) *loss = v / (float)B;
     }
-    if (tid == 0) *loss = red[0] / (float)B;
 }
 
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
@@ -1528,7 +1546,7 @@ int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const fl
     int rc = qnet_backward_launch(net, params, x, edge_src, edge_dst, node_ptr, edge_ptr, n_graphs, max_n, max_e, a, grad,
                                   workspace, stream);
     if (rc != MDQ_OK) return rc;
-    replay_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mode, scalar, q_other, action, reward, next_slot, batch,
+    replay_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mode, scalar, q_other, action, reward, next_slot, batch,
                                                            net->out_dim, gamma, loss);
     return mdq::check_launch("replay_loss_kernel");
 }
