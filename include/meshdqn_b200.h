@@ -74,6 +74,8 @@ typedef struct {
 /* Shared memory (bytes) the fused kernels need for graphs of at most max_n nodes / max_e edges
  * with `gpc` graphs per CTA; backward != 0 for the recompute+backward kernel.  Host-callable, no GPU. */
 int64_t mdq_qnet_smem_bytes(const mdq_net_t *net, int max_n, int max_e, int gpc, int backward);
+/* resident CTAs per SM of the forward (backward != 0: backward) kernel for these sizes (needs a device) */
+int mdq_qnet_occupancy(const mdq_net_t *net, int max_n, int max_e, int backward);
 /* graphs per CTA the forward launch will use for this batch (host-callable) */
 int mdq_qnet_pick_gpc(const mdq_net_t *net, int n_graphs, int max_n, int max_e);
 

@@ -83,6 +83,7 @@ _SIGS = {
     "mdq_launch_count": (c_int64, []),
     "mdq_qnet_set_trace": (None, [_P]),
     "mdq_qnet_smem_bytes": (c_int64, [POINTER(mdq_net_t), c_int, c_int, c_int, c_int]),
+    "mdq_qnet_occupancy": (c_int, [POINTER(mdq_net_t), c_int, c_int, c_int]),
     "mdq_qnet_pick_gpc": (c_int, [POINTER(mdq_net_t), c_int, c_int, c_int]),
     "mdq_qnet_forward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mdq_qnet_bwd_workspace_floats": (c_int64, [POINTER(mdq_net_t), c_int, c_int]),

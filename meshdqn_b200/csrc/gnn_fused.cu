@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int NT = 512;
+constexpr int NT = 256;  // 2 CTAs per SM (<= 113 KB shared memory, <= 128 registers each)
 constexpr int NWARP = NT / 32;
 constexpr int MAXB = MDQ_MAX_BLOCKS;
 constexpr int MLP_SPLIT = 4;
@@ -39,7 +39,8 @@ struct QLay {
     int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds, o_h1k, o_c1k;
     // weight stream: blocks >= 1 and the MLP read their weights from 16 KB shared-memory stages that one
     // thread fills with cp.async.bulk (TMA) in layer order, several chunks ahead of the consumers
-    int nstage, o_stage[MAX_STAGE], o_mbar, nchunks;
+    int nstage, o_stage[MAX_STAGE], o_mbar, nchunks;  // nstage == 0: weights are read straight from global memory
+    int fused;  // width 128: block 0 computes its TopK scores in the GEMM epilogue and never stores the hidden rows
     int ck_blk[MAXB], ck_lin[3], ck_blin[3], ck_bblk[MAXB];
     int total;  // 4-byte words
 };
@@ -130,34 +131,57 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     L.ymax = mdq::pad4(ymax);
     int o = 0;
     auto take = [&](int words) { int at = o; o += mdq::pad4(words); return at; };
-    L.o_w1 = take((L.KC1 + 1) * W);
-    L.o_cat1 = take(max_n * L.KC1);
-    // `big` holds block 0's hidden rows H1 [n][W]; once block 0 is done the same words hold block >= 1
-    // scratch: cat2 (forward and backward) and, in the backward kernel, dx / dp / dcat as well.
+    // the dense stages of blocks >= 1 give every thread one 4x4 output tile per pass; more rows than one pass
+    // covers are handled by re-reading the weights straight from global memory (no staged stream)
+    const bool multi_pass = ((gcap1 + 3) / 4) * (W / 4) > NT;
     const int dcat_a = G * L.ncap[nb > 1 ? 2 : 1] * 2 * W, dcat_c = gcap1 * W;
     const int dcat_words = dcat_a > dcat_c ? dcat_a : dcat_c;
+    // scratch of blocks >= 1 (and of the backward pass): cat2 [+ dx, dp, dcat]
     int alias_words = mdq::pad4(gcap1 * 2 * W);
     if (bwd) alias_words += mdq::pad4(L.xrows * W) + mdq::pad4(gcap1 * W) + mdq::pad4(dcat_words);
-    // the dense stages of blocks >= 1 give every thread one 4x4 output tile
-    if (((gcap1 + 3) / 4) * (W / 4) > NT) return MDQ_ESMEM;
-    const int big_words = mdq::pad4(max_n * W > alias_words ? max_n * W : alias_words);
-    L.o_big = take(big_words);
-    L.o_cat2 = L.o_big;
+    const int w1_words = mdq::pad4((L.KC1 + 1) * W), cat1_words = mdq::pad4(max_n * L.KC1);
+    L.fused = (W == 128) ? 1 : 0;
+    L.nstage = 0;
+    int n_dedicated = 0;
+    if (L.fused) {
+        // block 0 keeps no hidden rows: its staged weights and [agg|x] rows share one region with the scratch
+        // of the later blocks (they are never live at the same time)
+        const int l1_words = w1_words + cat1_words;
+        const int region = l1_words > alias_words ? l1_words : alias_words;
+        const int base = take(region);
+        L.o_w1 = base;
+        L.o_cat1 = base + w1_words;
+        L.o_big = base;  // unused
+        L.o_cat2 = base;
+        if (!bwd && !multi_pass) {  // forward: weight-stream stages = the region's tail + dedicated ones up to the 2-CTA/SM budget
+            for (int at = base + alias_words; at + STAGE_WORDS <= base + region && L.nstage < MAX_STAGE; at += STAGE_WORDS)
+                L.o_stage[L.nstage++] = at;
+            n_dedicated = L.nstage >= 1 ? 1 : 2;
+        }
+    } else {
+        L.o_w1 = take(w1_words);
+        L.o_cat1 = take(cat1_words);
+        // `big` holds block 0's hidden rows H1 [n][W]; afterwards the same words hold the later blocks' scratch
+        const int big_words = mdq::pad4(max_n * W > alias_words ? max_n * W : alias_words);
+        L.o_big = take(big_words);
+        L.o_cat2 = L.o_big;
+        if (!bwd && !multi_pass) {
+            if (w1_words >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_w1;
+            if (cat1_words >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_cat1;
+            for (int at = L.o_big + alias_words; at + STAGE_WORDS <= L.o_big + big_words && L.nstage < MAX_STAGE; at += STAGE_WORDS)
+                L.o_stage[L.nstage++] = at;
+            n_dedicated = L.nstage < 2 ? 2 - L.nstage : 0;
+        }
+    }
     if (bwd) {
         L.o_dx = L.o_cat2 + mdq::pad4(gcap1 * 2 * W);
         L.o_dp = L.o_dx + mdq::pad4(L.xrows * W);
         L.o_dcat = L.o_dp + mdq::pad4(gcap1 * W);
-        L.o_h1k = take(gcap1 * W);      // block 0's kept hidden rows, saved before `big` is reused
+        L.o_h1k = take(gcap1 * W);      // block 0's kept hidden rows
         L.o_c1k = take(gcap1 * L.KC1);  // ... and their input rows [agg | x]
     }
-    // weight-stream stages reuse what block 0 no longer needs: conv1's staged weights, cat1, the tail of `big`
-    L.nstage = 0;
-    if ((L.KC1 + 1) * W >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_w1;
-    if (max_n * L.KC1 >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_cat1;
-    for (int at = L.o_big + alias_words; at + STAGE_WORDS <= L.o_big + big_words && L.nstage < MAX_STAGE; at += STAGE_WORDS)
-        L.o_stage[L.nstage++] = at;
-    while (L.nstage < 2) L.o_stage[L.nstage++] = take(STAGE_WORDS);
-    L.o_mbar = take(2 * MAX_STAGE);
+    for (int i = 0; i < n_dedicated && L.nstage < MAX_STAGE; ++i) L.o_stage[L.nstage++] = take(STAGE_WORDS);
+    L.o_mbar = 0;
     L.o_xbuf = take(L.xrows * W);
     L.o_hbuf = take((bwd ? L.xrows : gcap1) * W);
     // edge endpoints / CSR columns are CTA-local row ids < 65536: stored as 16-bit, two per word
@@ -257,18 +281,18 @@ __device__ __forceinline__ float warp_sum(float v)
 __device__ __forceinline__ int topk_count_dev(float ratio, int n) { return __float2int_ru(__fmul_rn(ratio, (float)n)); }
 
 // Stable CSR by destination: rowptr[n+1], csr[E] = source of each in-edge, in edge_index order per row.
-// E <= 2*NT: every edge counts the earlier edges with its destination (its slot inside the row) in parallel;
+// E <= 4*NT: every edge counts the earlier edges with its destination (its slot inside the row) in parallel;
 // larger graphs fall back to one warp walking the edge list with match_any.
 __device__ void build_csr(int n, int E, const eid_t *es, const eid_t *ed, int *rowptr, int *cursor, eid_t *csr)
 {
     const int tid = threadIdx.x;
     for (int i = tid; i <= n; i += NT) cursor[i] = 0;
     __syncthreads();
-    const bool par = E <= 2 * NT;
-    int myrank[2] = {0, 0};
+    const bool par = E <= 4 * NT;
+    int myrank[4] = {0, 0, 0, 0};
     if (par) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 4; ++it) {
             const int e = tid + it * NT;
             if (e < E) {
                 const int d = ed[e];
@@ -319,7 +343,7 @@ __device__ void build_csr(int n, int E, const eid_t *es, const eid_t *ed, int *r
     __syncthreads();
     if (par) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 4; ++it) {
             const int e = tid + it * NT;
             if (e < E) csr[rowptr[ed[e]] + myrank[it]] = es[e];
         }
@@ -330,7 +354,7 @@ __device__ void build_csr(int n, int E, const eid_t *es, const eid_t *ed, int *r
 // out[r][c] = act(bias[c] + sum_k A[r][k] * WT[k][c]); 4x4 register tile, k ascending.
 template <bool W_SMEM>
 __device__ void dense_rows(int n, int K, const float *A, int lda, const float *WT, const float *bias, float *out,
-                           int ldo, int W, bool relu)
+                           int ldo, int W, bool relu, const int *rowidx = nullptr)
 {
     const int q = W >> 2;
     const int ngroups = (n + 3) >> 2;
@@ -340,7 +364,10 @@ __device__ void dense_rows(int n, int K, const float *A, int lda, const float *W
         const int r0 = rg << 2;
         const float *a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
+        for (int j = 0; j < 4; ++j) {
+            const int rr = min(r0 + j, n - 1);
+            a[j] = A + (size_t)(rowidx ? rowidx[rr] : rr) * lda;
+        }
         float acc[4][4];
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b4 = W_SMEM ? *reinterpret_cast<const float4 *>(bias + c4)
@@ -378,6 +405,61 @@ __device__ void dense_rows(int n, int K, const float *A, int lda, const float *W
     }
 }
 
+// Block 0 with W == 128: h = relu([agg|x] W + b) is never stored; each warp owns a 4-row group (32 lanes x 4
+// channels), folds h with the pooling weights and reduces over the warp:  z = (h . w) / ||w||, score = tanh(z).
+__device__ void dense1_score(int n, int K, const float *A, int lda, const float *WT, const float *bias,
+                             const float *__restrict__ pw_g, float *score, float *zval)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c4 = lane << 2;
+    const float4 pw = __ldg(reinterpret_cast<const float4 *>(pw_g + c4));
+    const float wnorm = sqrtf(warp_sum(fmaf(pw.x, pw.x, fmaf(pw.y, pw.y, fmaf(pw.z, pw.z, pw.w * pw.w)))));
+    const float4 b4 = *reinterpret_cast<const float4 *>(bias + c4);
+    const int ngroups = (n + 3) >> 2;
+    for (int rg = warp; rg < ngroups; rg += NWARP) {
+        const int r0 = rg << 2;
+        const float *a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+#pragma unroll 3
+        for (int k = 0; k < K; k += 4) {
+            float4 w[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4 *>(WT + (size_t)(k + kk) * 128 + c4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 xv = *reinterpret_cast<const float4 *>(a[j] + k);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    acc[j][0] = fmaf(xs[kk], w[kk].x, acc[j][0]);
+                    acc[j][1] = fmaf(xs[kk], w[kk].y, acc[j][1]);
+                    acc[j][2] = fmaf(xs[kk], w[kk].z, acc[j][2]);
+                    acc[j][3] = fmaf(xs[kk], w[kk].w, acc[j][3]);
+                }
+            }
+        }
+        float p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            p[j] = fmaxf(acc[j][0], 0.f) * pw.x;
+            p[j] = fmaf(fmaxf(acc[j][1], 0.f), pw.y, p[j]);
+            p[j] = fmaf(fmaxf(acc[j][2], 0.f), pw.z, p[j]);
+            p[j] = fmaf(fmaxf(acc[j][3], 0.f), pw.w, p[j]);
+            p[j] = warp_sum(p[j]);
+        }
+        if (lane < 4 && r0 + lane < n) {
+            const float dot = lane == 0 ? p[0] : (lane == 1 ? p[1] : (lane == 2 ? p[2] : p[3]));
+            const float z = dot / wnorm;
+            zval[r0 + lane] = z;
+            score[r0 + lane] = tanhf(z);
+        }
+    }
+}
+
 // ---- weight stream: cp.async (LDGSTS, 16 B per thread) global -> shared, ns-1 chunks in flight ----
 // (A single-thread cp.async.bulk / TMA version measured ~12 B/clk per SM here -- latency-bound on its few
 // outstanding requests -- so every thread issues its own 16-byte asynchronous copies instead.)
@@ -406,6 +488,7 @@ struct WStream {
     // every thread copies its 16-byte units of chunk j and commits one group (empty past the last chunk)
     __device__ __forceinline__ void issue(int j) const
     {
+        if (ns == 0) return;
         if (j < nchunks) {
             const int units = (ck->rows[j] * ck->cols[j]) >> 2;
             const float *src = params + ck->off[j];
@@ -422,6 +505,7 @@ struct WStream {
     __device__ __forceinline__ const float *wait(int j) const
     {
         stamp(j, 0);
+        if (ns == 0) return params + ck->off[j];  // direct mode: the consumer reads global memory (L1/L2)
         switch (ns) {
             case 2: cp_async_wait<0>(); break;
             case 3: cp_async_wait<1>(); break;
@@ -446,53 +530,56 @@ __device__ void dense_stream(const WStream &ws, int j0, int n, int K, const floa
 {
     const int q = W >> 2;
     const int ngroups = (n + 3) >> 2;
-    const int item = threadIdx.x;
-    const bool active = item < ngroups * q;
-    const int rg = active ? item / q : 0;
-    const int c4 = active ? (item - rg * q) << 2 : 0;
-    const int r0 = rg << 2;
-    const float *a[4];
+    const int gpp = NT / q;  // row groups per pass (a second pass only happens in direct mode, ws.ns == 0)
+    for (int g0 = 0; g0 < ngroups; g0 += gpp) {
+        const int item = threadIdx.x;
+        const bool active = item < min(gpp, ngroups - g0) * q;
+        const int rg = g0 + (active ? item / q : 0);
+        const int c4 = active ? (item % q) << 2 : 0;
+        const int r0 = rg << 2;
+        const float *a[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
-    float acc[4][4];
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias && active) b4 = __ldg(reinterpret_cast<const float4 *>(bias + c4));
+        for (int j = 0; j < 4; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
+        float acc[4][4];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && active) b4 = __ldg(reinterpret_cast<const float4 *>(bias + c4));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
-    int k = 0;
-    for (int jc = j0; k < K; ++jc) {
-        const float *st = ws.wait(jc);
-        const int rows = ws.rows(jc);
-        if (active) {
+        for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+        int k = 0;
+        for (int jc = j0; k < K; ++jc) {
+            const float *st = ws.wait(jc);
+            const int rows = ws.rows(jc);
+            if (active) {
 #pragma unroll 2
-            for (int kk = 0; kk < rows; kk += 4) {
-                float4 w[4];
+                for (int kk = 0; kk < rows; kk += 4) {
+                    float4 w[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) w[t] = *reinterpret_cast<const float4 *>(st + (size_t)(kk + t) * W + c4);
+                    for (int t = 0; t < 4; ++t) w[t] = *reinterpret_cast<const float4 *>(st + (size_t)(kk + t) * W + c4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 xv = *reinterpret_cast<const float4 *>(a[j] + k + kk);
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(a[j] + k + kk);
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        acc[j][0] = fmaf(xs[t], w[t].x, acc[j][0]);
-                        acc[j][1] = fmaf(xs[t], w[t].y, acc[j][1]);
-                        acc[j][2] = fmaf(xs[t], w[t].z, acc[j][2]);
-                        acc[j][3] = fmaf(xs[t], w[t].w, acc[j][3]);
+                        for (int t = 0; t < 4; ++t) {
+                            acc[j][0] = fmaf(xs[t], w[t].x, acc[j][0]);
+                            acc[j][1] = fmaf(xs[t], w[t].y, acc[j][1]);
+                            acc[j][2] = fmaf(xs[t], w[t].z, acc[j][2]);
+                            acc[j][3] = fmaf(xs[t], w[t].w, acc[j][3]);
+                        }
                     }
                 }
             }
+            k += rows;
+            ws.release(jc);
         }
-        k += rows;
-        ws.release(jc);
-    }
-    if (active) {
+        if (active) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (r0 + j < n) {
-                float4 o4 = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
-                *reinterpret_cast<float4 *>(out + (size_t)(r0 + j) * ldo + c4) = o4;
+            for (int j = 0; j < 4; ++j) {
+                if (r0 + j < n) {
+                    float4 o4 = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+                    *reinterpret_cast<float4 *>(out + (size_t)(r0 + j) * ldo + c4) = o4;
+                }
             }
         }
     }
@@ -576,7 +663,7 @@ __device__ void matmul_t_stream(const WStream &ws, int j0, int K, int C, int nr,
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QArgs a)
+__global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QArgs a)
 {
     extern __shared__ __align__(16) float smem[];
     const QLay &L = a.L;
@@ -727,11 +814,17 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
         }
         __syncthreads();
         MDQ_TRACE();  // L1: aggregated
-        dense_rows<true>(n, KC1, cat1, KC1, w1s, w1s + KC1 * W, big, W, W, true);
-        __syncthreads();
-        MDQ_TRACE();  // L1: dense
-        compute_scores(0, n, big, 0);
-        __syncthreads();
+        if (L.fused) {
+            dense1_score(n, KC1, cat1, KC1, w1s, w1s + KC1 * W, P + net.blk[0].pool_off, score, zval);
+            __syncthreads();
+            MDQ_TRACE();  // L1: dense
+        } else {
+            dense_rows<true>(n, KC1, cat1, KC1, w1s, w1s + KC1 * W, big, W, W, true);
+            __syncthreads();
+            MDQ_TRACE();  // L1: dense
+            compute_scores(0, n, big, 0);
+            __syncthreads();
+        }
         MDQ_TRACE();  // L1: scores
         const int k = topk_count_dev(net.ratio, n);
         const int obase = seg[1 * (G + 1) + gi];
@@ -755,12 +848,20 @@ __global__ void __launch_bounds__(NT, 1) qnet_kernel(const __grid_constant__ QAr
         {
             float *xo = xbuf + (size_t)(L.rowoff[1] + obase) * W;
             const int *par = parent + L.n_max + L.rowoff[1] + obase;
-            for (int idx = tid; idx < k * W; idx += NT) {
-                const int r = idx / W, c = idx - r * W;
-                const int i = par[r];
-                const float h = big[(size_t)i * W + c];
-                xo[idx] = h * score[i];
-                if (BWD) (smem + L.o_h1k)[(size_t)(obase + r) * W + c] = h;
+            if (L.fused) {
+                // recompute the hidden rows of the k kept nodes only (same code path, bit-identical)
+                float *hk = (BWD ? smem + L.o_h1k : hbuf) + (size_t)obase * W;
+                dense_rows<true>(k, KC1, cat1, KC1, w1s, w1s + KC1 * W, hk, W, W, true, par);
+                __syncthreads();
+                for (int idx = tid; idx < k * W; idx += NT) xo[idx] = hk[idx] * score[par[idx / W]];
+            } else {
+                for (int idx = tid; idx < k * W; idx += NT) {
+                    const int r = idx / W, c = idx - r * W;
+                    const int i = par[r];
+                    const float h = big[(size_t)i * W + c];
+                    xo[idx] = h * score[i];
+                    if (BWD) (smem + L.o_h1k)[(size_t)(obase + r) * W + c] = h;
+                }
             }
             if (BWD)
                 for (int idx = tid; idx < k * KC1; idx += NT) {
@@ -1402,6 +1503,8 @@ int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLa
         return MDQ_ESMEM;
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess)  // ask for the largest shared-memory carve-out so two ~110 KB CTAs fit one SM
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { mdq::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
     return MDQ_OK;
 }
@@ -1424,16 +1527,39 @@ int64_t mdq_qnet_smem_bytes(const mdq_net_t *net, int max_n, int max_e, int gpc,
     return (int64_t)L.total * 4;
 }
 
+int mdq_qnet_occupancy(const mdq_net_t *net, int max_n, int max_e, int backward)
+{
+    QLay L;
+    WChunks ck;
+    int rc = backward ? setup_launch(net, max_n, max_e, 1, 1, L, &ck, qnet_kernel<true>)
+                      : setup_launch(net, max_n, max_e, 1, 0, L, &ck, qnet_kernel<false>);
+    if (rc != MDQ_OK) return rc;
+    int nblk = 0;
+    cudaError_t e = backward ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, qnet_kernel<true>, NT, (size_t)L.total * 4)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, qnet_kernel<false>, NT, (size_t)L.total * 4);
+    if (e != cudaSuccess) { mdq::set_error("occupancy query: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
+    return nblk;
+}
+
 int mdq_qnet_pick_gpc(const mdq_net_t *net, int n_graphs, int max_n, int max_e)
 {
-    // smallest graphs-per-CTA that brings the grid to one wave of 148 CTAs, limited by shared memory
+    // fewest waves over 148 SMs; CTAs/SM follows from shared memory (228 KB/SM, 1 KB reserved per CTA) and the
+    // 128-register launch bound (<= 2); ties -> fewer graphs per CTA (shorter dependent chain per CTA)
     int best = 1;
+    long best_waves = -1;
     for (int G = 1; G <= 4; ++G) {
         QLay L;
         if (build_layout(*net, max_n, max_e, G, 0, L) != MDQ_OK) break;
-        if ((size_t)L.total * 4 > 227 * 1024) break;
-        best = G;
-        if ((n_graphs + G - 1) / G <= 148) break;
+        const size_t bytes = (size_t)L.total * 4;
+        if (bytes > 227 * 1024) break;
+        int per_sm = (int)((228 * 1024) / (bytes + 1024));
+        if (per_sm > 2) per_sm = 2;
+        if (per_sm < 1) per_sm = 1;
+        const long ctas = (n_graphs + G - 1) / G;
+        const long waves = (ctas + 148L * per_sm - 1) / (148L * per_sm);
+        // cost ~ waves * graphs per CTA (a CTA walks its graphs' first block one after the other)
+        const long cost = waves * G;
+        if (best_waves < 0 || cost < best_waves) { best_waves = cost; best = G; }
     }
     return best;
 }

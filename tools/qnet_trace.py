@@ -14,7 +14,9 @@ FWD = ["start", "L1 load", "L1 csr", "L1 agg", "L1 dense", "L1 scores", "L1 rank
        "B1 csr", "B1 conv", "B1 pool", "B2 csr", "B2 conv", "B2 pool", "B3 csr", "B3 conv", "B3 pool", "MLP", "softmax"]
 BWD = FWD + ["bwd MLP", "bwd B3 start", "bwd B2 start", "bwd B1 start", "bwd B0 start", "bwd done"]
 L = _lib.lib()
-for B in (1,):
+net._ensure_packed(); net._net.x_stride = 17
+print('occupancy CTAs/SM fwd', L.mdq_qnet_occupancy(net._net, 180, 372, 0), 'bwd', L.mdq_qnet_occupancy(net._net, 180, 372, 1))
+for B in (1, 256):
     b = Batch.from_data_list([mk() for _ in range(B)]).to(dev)
     tr = torch.zeros(512, dtype=torch.int64, device=dev)
     for mode, names in (("fwd", FWD), ("bwd", BWD)):
@@ -39,3 +41,24 @@ for B in (1,):
             for j in range(30):
                 nxt = f[j + 1, 0] - f[j, 2] if j + 1 < 30 else 0
                 print(f"   {j:3d} {f[j,1]-f[j,0]:8d} {f[j,2]-f[j,1]:8d} {nxt:8d}")
+
+# ---- launch-level timing: back-to-back vs interleaved with an unrelated (small-carveout) kernel ----
+b = Batch.from_data_list([mk() for _ in range(256)]).to(dev)
+args = net._prep(b)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+small = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+def timeit(fn, pre=None, n=20):
+    tot = 0.0
+    for _ in range(n):
+        if pre is not None:
+            pre()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return 1000 * tot / n
+with torch.no_grad():
+    f = lambda: net._launch_forward(*args, False, True)
+    for _ in range(3): f()
+    print("fwd B=256 back-to-back        : %.1f us" % timeit(f))
+    print("fwd B=256 after small fill    : %.1f us" % timeit(f, lambda: small.fill_(1)))
+    print("fwd B=256 after 256MB L2 flush: %.1f us" % timeit(f, lambda: flush.fill_(1)))
