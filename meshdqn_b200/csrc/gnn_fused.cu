@@ -11,6 +11,7 @@
 // Message passing is a stable CSR-by-destination gather (edges keep their edge_index order inside a row,
 // as torch_scatter's CPU loop does), mean / GCN-normalised, fp32, sequential per row.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mdq_common.cuh"
@@ -143,6 +144,11 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     L.fused = (W == 128) ? 1 : 0;
     L.nstage = 0;
     int n_dedicated = 0;
+    // The cp.async stage ring is kept for experiments (MDQ_QNET_STAGED=1).  Measured on B200 at 256 threads and
+    // 2 CTAs/SM, reading the weights straight from L2 with 16-byte loads (8+ in flight per thread) is faster than
+    // staging them (per-chunk barrier + LDGSTS issue cost ~800 cycles per 16 KB), so direct mode is the default.
+    static const bool staged_env = [] { const char *e = getenv("MDQ_QNET_STAGED"); return e && e[0] == '1'; }();
+    const bool want_stages = staged_env && !bwd && !multi_pass;
     if (L.fused) {
         // block 0 keeps no hidden rows: its staged weights and [agg|x] rows share one region with the scratch
         // of the later blocks (they are never live at the same time)
@@ -153,7 +159,7 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
         L.o_cat1 = base + w1_words;
         L.o_big = base;  // unused
         L.o_cat2 = base;
-        if (!bwd && !multi_pass) {  // forward: weight-stream stages = the region's tail + dedicated ones up to the 2-CTA/SM budget
+        if (want_stages) {  // forward: weight-stream stages = the region's tail + dedicated ones up to the 2-CTA/SM budget
             for (int at = base + alias_words; at + STAGE_WORDS <= base + region && L.nstage < MAX_STAGE; at += STAGE_WORDS)
                 L.o_stage[L.nstage++] = at;
             n_dedicated = L.nstage >= 1 ? 1 : 2;
@@ -165,7 +171,7 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
         const int big_words = mdq::pad4(max_n * W > alias_words ? max_n * W : alias_words);
         L.o_big = take(big_words);
         L.o_cat2 = L.o_big;
-        if (!bwd && !multi_pass) {
+        if (want_stages) {
             if (w1_words >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_w1;
             if (cat1_words >= STAGE_WORDS) L.o_stage[L.nstage++] = L.o_cat1;
             for (int at = L.o_big + alias_words; at + STAGE_WORDS <= L.o_big + big_words && L.nstage < MAX_STAGE; at += STAGE_WORDS)
@@ -203,7 +209,7 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     L.o_ecnt = take(nb + 1);
     L.o_racc = take(G * 2 * W);
     L.o_y = take(G * 3 * L.ymax);
-    L.o_part = take(MLP_SPLIT * G * L.ymax);
+    L.o_part = take(8 * G * L.ymax);
     if (bwd) {
         L.o_dr = take(2 * W + 3 * L.ymax);
         L.o_amax = take(nb * G * W);
@@ -590,6 +596,37 @@ __device__ void dense_stream(const WStream &ws, int j0, int n, int K, const floa
 __device__ void mlp_stream(const WStream &ws, int j0, int rows, int K, int O, const float *in, int ldi,
                            const float *__restrict__ b, float *out, int ldo, bool relu, float *part)
 {
+    if (ws.ns == 0 && rows == 1 && (O & 3) == 0 && (O >> 2) <= NT) {
+        // direct mode, one row: thread = (4 output columns, k-slice); 16-byte coalesced weight loads, 8 in flight
+        const float *WT = ws.params + ws.ck->off[j0];
+        const int Q = O >> 2;
+        int SLd = NT / Q;
+        SLd = SLd >= 8 ? 8 : (SLd >= 4 ? 4 : (SLd >= 2 ? 2 : 1));
+        while (K % SLd) SLd >>= 1;
+        const int per = K / SLd;
+        if (threadIdx.x < Q * SLd) {
+            const int sl = threadIdx.x / Q, qd = threadIdx.x - sl * Q;
+            const float4 *wp = reinterpret_cast<const float4 *>(WT + (size_t)(sl * per) * O) + qd;
+            const float *xi = in + sl * per;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int kk = 0; kk < per; ++kk) {
+                const float4 w = __ldg(wp + (size_t)kk * Q);
+                const float xv = xi[kk];
+                acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y);
+                acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+            }
+            *reinterpret_cast<float4 *>(part + (size_t)sl * O + 4 * qd) = acc;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < O; c += NT) {
+            float v = __ldg(b + c);
+            for (int sl = 0; sl < SLd; ++sl) v += part[sl * O + c];
+            out[c] = relu ? fmaxf(v, 0.f) : v;
+        }
+        __syncthreads();
+        return;
+    }
     const int RO = rows * O;
     const int fit = NT / RO;
     const int SL = fit >= 4 ? 4 : (fit >= 2 ? 2 : 1);
@@ -616,7 +653,7 @@ __device__ void mlp_stream(const WStream &ws, int j0, int rows, int K, int O, co
                 const float *xi = in + r_[it] * ldi + k + s_[it] * per;
                 const float *wp = st + (size_t)(s_[it] * per) * O + c_[it];
                 float av = acc[it];
-#pragma unroll 4
+#pragma unroll 16
                 for (int kk = 0; kk < per; ++kk) av = fmaf(xi[kk], wp[(size_t)kk * O], av);
                 acc[it] = av;
             }
@@ -642,6 +679,32 @@ __device__ void matmul_t_stream(const WStream &ws, int j0, int K, int C, int nr,
                                 const float *gate)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ws.ns == 0 && (C & 3) == 0) {
+        // direct mode: one thread per weight row k (rows are contiguous in memory, 16-byte loads, many in flight),
+        // delta rows broadcast from shared memory; two delta rows per pass
+        const float *WT = ws.params + ws.ck->off[j0];
+        for (int r0 = 0; r0 < nr; r0 += 2) {
+            const bool two = r0 + 1 < nr;
+            const float *d0 = D + (size_t)r0 * ldd, *d1 = D + (size_t)(two ? r0 + 1 : r0) * ldd;
+            for (int k = threadIdx.x; k < K; k += NT) {
+                const float4 *wrow = reinterpret_cast<const float4 *>(WT + (size_t)k * C);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+                for (int c4 = 0; c4 < (C >> 2); ++c4) {
+                    const float4 w = __ldg(wrow + c4);
+                    const float4 x0 = *reinterpret_cast<const float4 *>(d0 + 4 * c4);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(d1 + 4 * c4);
+                    a0 = fmaf(x0.x, w.x, a0); a0 = fmaf(x0.y, w.y, a0); a0 = fmaf(x0.z, w.z, a0); a0 = fmaf(x0.w, w.w, a0);
+                    a1 = fmaf(x1.x, w.x, a1); a1 = fmaf(x1.y, w.y, a1); a1 = fmaf(x1.z, w.z, a1); a1 = fmaf(x1.w, w.w, a1);
+                }
+                const bool on = (gate == nullptr || gate[k] > 0.f);
+                out[(size_t)r0 * ldo + k] = on ? a0 : 0.f;
+                if (two) out[(size_t)(r0 + 1) * ldo + k] = on ? a1 : 0.f;
+            }
+        }
+        __syncthreads();
+        return;
+    }
     int k = 0;
     for (int jc = j0; k < K; ++jc) {
         const float *st = ws.wait(jc);
@@ -1437,28 +1500,35 @@ __global__ void __launch_bounds__(1024) replay_loss_kernel(int mode, const float
 {
     __shared__ float red[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float lsum = 0.f;  // meaningful in lane 0
-    for (int b = warp; b < B; b += 32) {
-        const int slot = next_slot[b];
-        float pred, nsv = 0.f;
+    const int sub = tid & 3;  // 4 lanes per transition: 256 transitions per pass, their q rows read concurrently
+    float lsum = 0.f;         // meaningful where sub == 0
+    for (int b0 = 0; b0 < B; b0 += 256) {
+        const int b = b0 + (tid >> 2);
+        const bool ok = b < B;
+        const int slot = ok ? next_slot[b] : -1;
+        float pred = 0.f, nsv = 0.f;
         if (mode == 1) {
-            pred = scalar[b];
+            if (ok) pred = scalar[b];
+            float m = -INFINITY;
             if (slot >= 0) {
                 const float *q = qother + (size_t)slot * A;
-                float m = -INFINITY;
-                for (int c = lane; c < A; c += 32) m = fmaxf(m, q[c]);
-#pragma unroll
-                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
-                nsv = m;
+#pragma unroll 8
+                for (int c = sub; c < A; c += 4) m = fmaxf(m, __ldg(q + c));
             }
-        } else {
+            m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
+            nsv = slot >= 0 ? m : 0.f;
+        } else if (ok) {
             pred = qother[(size_t)b * A + action[b]];
             if (slot >= 0) nsv = scalar[slot];
         }
-        const float d = pred - (nsv * gamma + reward[b]);
-        const float ad = fabsf(d);
-        lsum += (ad < 1.f) ? 0.5f * d * d : (ad - 0.5f);
+        if (ok && sub == 0) {
+            const float d = pred - (nsv * gamma + reward[b]);
+            const float ad = fabsf(d);
+            lsum += (ad < 1.f) ? 0.5f * d * d : (ad - 0.5f);
+        }
     }
+    lsum = warp_sum(lsum);
     if (lane == 0) red[warp] = lsum;
     __syncthreads();
     if (warp == 0) {
