@@ -189,6 +189,39 @@ int mdq_interpolate(const double *coords, int nv, const int32_t *edges, int ne, 
                     const double *U0, const double *P0, double *U, double *P, int32_t *cell_of,
                     int32_t *miss_count, int32_t *miss_list, void *stream);
 
+/* Tiled re-interpolation for large source meshes (same results as mdq_interpolate, bit for bit).
+ * The index over M0 is built once on the host (meshdqn_b200/tile_index.py): k-d leaves of ~256 cells whose whole
+ * working set (local coordinates, all T snapshots' P2/P1 coefficients, cell->dof table, micro-grid) is contiguous,
+ * so one CTA stages a leaf in shared memory with bulk (TMA) copies and serves every target point inside it. */
+typedef struct {
+    int32_t n_leaves, depth, T;
+    int32_t max_nv, max_np2, max_nc, max_nbin, max_nent; /* padded per-leaf maxima (shared-memory sizing) */
+    int64_t u_stride, p_stride;                          /* rows of UL / PL per snapshot */
+    const double *tree;         /* [n_leaves-1] split planes, heap order, split axis in the mantissa LSB */
+    const int32_t *leaf_info;   /* [n_leaves][16] */
+    const double *leaf_rect;    /* [n_leaves][4] micro-grid x0, y0, 1/dx, 1/dy */
+    const double *coordsL;      /* [sum nv][2] */
+    const double *UL;           /* [T][u_stride][2] */
+    const double *PL;           /* [T][p_stride] */
+    const int32_t *gidL;        /* [sum nc] global cell ids, ascending per leaf */
+    const uint16_t *cvL;        /* [sum nc][6] local dof ids (3 vertices, 3 edges) */
+    const uint16_t *binptrL;    /* micro-grid CSR pointers */
+    const uint16_t *binsL;      /* micro-grid candidate lists (local cell ids, ascending) */
+} mdq_tile_index_t;
+
+/* int32 words of workspace mdq_interpolate_tiled needs for np = nv + ne target points */
+int64_t mdq_interp_tiled_workspace_words(const mdq_tile_index_t *idx, int np);
+/* shared memory (bytes) one CTA of the tiled kernel uses; host-callable */
+int64_t mdq_interp_tiled_smem_bytes(const mdq_tile_index_t *idx);
+
+/* Same contract as mdq_interpolate (targets, outputs, miss list); coords0/cells0/cell_edges0/U0/P0 are only
+ * touched by the closest-cell fallback for points outside every source cell. */
+int mdq_interpolate_tiled(const double *coords, int nv, const int32_t *edges, int ne, const mdq_tile_index_t *idx,
+                          const double *coords0, const int32_t *cells0, const int32_t *cell_edges0, int nv0, int ne0,
+                          int nc0, const double *U0, const double *P0, double tol, double *U, double *P,
+                          int32_t *cell_of, int32_t *miss_count, int32_t *miss_list, int32_t *workspace,
+                          void *stream);
+
 /* DragProbe/LiftProbe.sample for T <= 8 snapshots (probes.py:23-31,43-50): sum over exterior facets with
  * tag == 1 of |f| (sigma(m_f) n).e_x / e_y.  drag_lift [2][T] f64.  Deterministic fixed-shape reduction. */
 int mdq_drag_lift(const double *coords, const int32_t *cells, const int32_t *cell_edges, int nv, int ne,

@@ -58,8 +58,14 @@ class SourceField:
     P0 f64 [T][V0]; grid bins hold the ids of the cells whose inflated bounding box overlaps them.
     """
 
-    def __init__(self, mesh: DeviceMesh, U0, P0, bins_per_cell=4.0):
+    TILED_MIN_CELLS = 16384   # below this the uniform-grid kernel (one launch) has the lower latency
+
+    def __init__(self, mesh: DeviceMesh, U0, P0, bins_per_cell=4.0, tiled=None, leaf_cells=256, micro_bins_per_cell=4.0):
         self.mesh = mesh
+        self.tiled = (mesh.nc >= self.TILED_MIN_CELLS) if tiled is None else bool(tiled)
+        self.leaf_cells = int(leaf_cells)
+        self.micro_bins_per_cell = float(micro_bins_per_cell)
+        self.tile = None
         d = mesh.device
         self.U0 = torch.as_tensor(np.ascontiguousarray(U0, dtype=np.float64)).to(d).contiguous()
         self.P0 = torch.as_tensor(np.ascontiguousarray(P0, dtype=np.float64)).to(d).contiguous()
@@ -90,6 +96,31 @@ class SourceField:
             _lib.check(L.mdq_grid_fill(p(mesh.coords), p(mesh.cells), mesh.nc, self.h_grid, p(self.bin_ptr), p(cnt),
                                        p(self.bin_cells), st), "mdq_grid_fill")
         self.n_bin_entries = total
+        if self.tiled:
+            self._build_tiles(U0, P0)
+
+    def _build_tiles(self, U0, P0):
+        """Leaf-packed copy of M0 for the tiled kernel (tile_index.py); built once, M0 never changes (quirk B6)."""
+        from .tile_index import build_tile_index
+        m, d = self.mesh, self.mesh.device
+        ti = build_tile_index(m.coordinates(), m.cells_host(), m.cell_edges.cpu().numpy(), m.ne,
+                              np.asarray(U0, dtype=np.float64), np.asarray(P0, dtype=np.float64), self.leaf_cells,
+                              bins_per_cell=self.micro_bins_per_cell)
+        self.tile_host = ti
+        dev = {k: torch.from_numpy(np.ascontiguousarray(getattr(ti, k))).to(d)
+               for k in ("tree", "leaf_info", "leaf_rect", "coordsL", "UL", "PL", "gidL")}
+        for k in ("cvL", "binptrL", "binsL"):      # uint16 payloads travel as raw int16 bits
+            dev[k] = torch.from_numpy(np.ascontiguousarray(getattr(ti, k)).view(np.int16)).to(d)
+        self._tile_dev = dev
+        c = _lib.mdq_tile_index_t()
+        c.n_leaves, c.depth, c.T = ti.n_leaves, ti.depth, ti.T
+        c.max_nv, c.max_np2, c.max_nc, c.max_nbin, c.max_nent = ti.max_nv, ti.max_np2, ti.max_nc, ti.max_nbin, ti.max_nent
+        c.u_stride, c.p_stride = ti.u_stride, ti.p_stride
+        for k, t in dev.items():
+            setattr(c, k, t.data_ptr())
+        self.tile = c
+        self.tile_bytes = ti.nbytes()
+        self.tile_smem = int(_lib.lib().mdq_interp_tiled_smem_bytes(ctypes.byref(c)))
 
     def interpolate(self, target: DeviceMesh, tol=1e-12):
         """``Function.interpolate`` of every snapshot onto ``target`` (Env2DAirfoil.py:556-568).
@@ -106,6 +137,16 @@ class SourceField:
         miss_list = torch.empty(npt, dtype=torch.int32, device=d)
         L = _lib.lib()
         p = _lib.ptr
+        if self.tile is not None:
+            words = int(L.mdq_interp_tiled_workspace_words(ctypes.byref(self.tile), npt))
+            ws = torch.empty(words, dtype=torch.int32, device=d)
+            with torch.cuda.device(d):
+                rc = L.mdq_interpolate_tiled(p(target.coords), target.nv, p(target.edges), target.ne,
+                                             ctypes.byref(self.tile), p(m0.coords), p(m0.cells), p(m0.cell_edges), m0.nv,
+                                             m0.ne, m0.nc, p(self.U0), p(self.P0), float(tol), p(U), p(P), p(cell_of),
+                                             p(miss), p(miss_list), p(ws), _lib.stream_ptr())
+            _lib.check(rc, "mdq_interpolate_tiled")
+            return U, P, cell_of, miss
         with torch.cuda.device(d):
             rc = L.mdq_interpolate(p(target.coords), target.nv, p(target.edges), target.ne, p(m0.coords), p(m0.cells),
                                    p(m0.cell_edges), m0.nv, m0.ne, m0.nc, self.h_grid, p(self.bin_ptr), p(self.bin_cells),

@@ -44,6 +44,14 @@ class mdq_net_t(Structure):
                 ("n_params", c_int32), ("blk", mdq_block_t * MDQ_MAX_BLOCKS)]
 
 
+class mdq_tile_index_t(Structure):
+    _fields_ = [("n_leaves", c_int32), ("depth", c_int32), ("T", c_int32), ("max_nv", c_int32), ("max_np2", c_int32),
+                ("max_nc", c_int32), ("max_nbin", c_int32), ("max_nent", c_int32), ("u_stride", c_int64),
+                ("p_stride", c_int64), ("tree", c_void_p), ("leaf_info", c_void_p), ("leaf_rect", c_void_p),
+                ("coordsL", c_void_p), ("UL", c_void_p), ("PL", c_void_p), ("gidL", c_void_p), ("cvL", c_void_p),
+                ("binptrL", c_void_p), ("binsL", c_void_p)]
+
+
 def _newer(src, dst):
     return (not os.path.exists(dst)) or os.path.getmtime(src) > os.path.getmtime(dst)
 
@@ -101,6 +109,10 @@ _SIGS = {
     "mdq_grid_fill": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
     "mdq_interpolate": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, POINTER(c_double), _P, _P,
                                 c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mdq_interp_tiled_workspace_words": (c_int64, [POINTER(mdq_tile_index_t), c_int]),
+    "mdq_interp_tiled_smem_bytes": (c_int64, [POINTER(mdq_tile_index_t)]),
+    "mdq_interpolate_tiled": (c_int, [_P, c_int, _P, c_int, POINTER(mdq_tile_index_t), _P, _P, _P, c_int, c_int, c_int,
+                                      _P, _P, c_double, _P, _P, _P, _P, _P, _P, _P]),
     "mdq_drag_lift": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_double, _P, _P]),
     "mdq_build_state": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P,
                                 _P, _P, c_int, _P, _P]),

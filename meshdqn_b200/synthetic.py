@@ -76,12 +76,26 @@ def _naca_ring(n, chord=1.0, t=0.12, m=0.0, pc=0.4, x0=0.0, y0=0.0):
     return ring
 
 
-def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None):
+def _morton_order(q, lo, hi, bits=16):
+    """Z-curve rank of points [n,2] (locality-preserving numbering, as mesh generators produce)."""
+    s = ((q - lo) / (hi - lo) * ((1 << bits) - 1)).astype(np.uint64)
+    def spread(v):
+        v = (v | (v << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return v
+    return np.argsort(spread(s[:, 0]) | (spread(s[:, 1]) << np.uint64(1)), kind="stable")
+
+
+def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None, order="random"):
     """Graded Delaunay mesh of the channel [-0.5,3]x[-0.5,0.5] minus a NACA-style hole.
 
     Cells whose three vertices are all boundary points are dropped, the same rule the
     reference applies after re-triangulating (Env2DAirfoil.py:496).  Returns
-    ``(coords f64 [V,2], cells i32 [C,3], n_ring)``.
+    ``(coords f64 [V,2], cells i32 [C,3], n_ring)``.  ``order="morton"`` numbers the interior vertices along a
+    Z-curve (the locality a front/quadtree mesh generator gives); ``"random"`` keeps the sampling order.
     """
     from scipy.spatial import Delaunay
 
@@ -163,6 +177,10 @@ def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None):
         pts.append(q)
         got += len(q)
     interior = np.concatenate([buffer_pts] + pts, 0)[:n_int + len(buffer_pts)]
+    if order == "morton":
+        interior = interior[_morton_order(interior, np.array([-0.5, -0.5]), np.array([3.0, 0.5]))]
+    elif order != "random":
+        raise ValueError("order must be 'random' or 'morton'")
     coords = np.concatenate([corners, ring, walls, interior], 0)
     tri = Delaunay(coords)
     cells = tri.simplices

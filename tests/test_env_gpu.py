@@ -158,3 +158,65 @@ def test_interpolation_on_synthetic_mesh_with_random_removals(cuda_device):
     assert np.array_equal(Un[1], -Un[0])                              # linearity, bit-exact
     U2, P2, cell2, _ = src.interpolate(m1)
     assert torch.equal(U2, U) and torch.equal(P2, P) and torch.equal(cell2, cell_of)
+
+
+def _coarsened(coords, cells_topo, n_drop, seed, dev):
+    """Target mesh for interpolation tests: drop interior vertices, re-triangulate, apply the reference's cell rule."""
+    from meshdqn_b200.flow_solver import DeviceMesh
+    from scipy.spatial import Delaunay
+    rng = np.random.RandomState(seed)
+    interior = np.nonzero(~cells_topo.on_boundary)[0]
+    keep = np.ones(len(coords), bool)
+    keep[rng.choice(interior, n_drop, replace=False)] = False
+    c2 = coords[keep]
+    newid = np.cumsum(keep) - 1
+    isb = np.zeros(len(c2), bool)
+    isb[newid[cells_topo.boundary_vertices]] = True
+    t2 = Delaunay(c2).simplices
+    t2 = t2[isb[t2].sum(1) != 3]
+    return c2, t2, DeviceMesh(c2, t2, dev)
+
+
+@pytest.mark.parametrize("case", ["ys930_leaf64", "synthetic_leaf256", "synthetic_oversized_leaf"])
+def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, case):
+    """The tiled (k-d leaf, TMA-staged) kernel must return the same cell ids and the same field bits as the
+    uniform-grid kernel, and the oracle's brute-force cell ids."""
+    from meshdqn_b200.Env2DAirfoil import SourceField
+    from meshdqn_b200.flow_solver import DeviceMesh
+    from meshdqn_b200.synthetic import synthetic_airfoil_mesh, synthetic_fields
+    if case == "ys930_leaf64":
+        coords, cells = load_mesh("ys930")
+        topo0 = geom.Topology(cells, len(coords))
+        coords = geom.smooth(coords, topo0, 50)
+        leaf, ndrop = 64, 12
+    else:
+        coords, cells, _ = synthetic_airfoil_mesh(20000, seed=2)
+        topo0 = geom.Topology(cells, len(coords))
+        leaf, ndrop = (256, 150) if case == "synthetic_leaf256" else (8192, 150)
+    U0, P0 = synthetic_fields(coords, topo0.edges, 5, 1)
+    m0 = DeviceMesh(coords, cells, cuda_device)
+    if case == "synthetic_oversized_leaf":
+        with pytest.raises(RuntimeError, match="shared memory"):       # 5k-cell leaves exceed 227 KB: loud failure
+            SourceField(m0, U0, P0, tiled=True, leaf_cells=leaf).interpolate(m0)
+        return
+    grid = SourceField(m0, U0, P0, tiled=False)
+    tiled = SourceField(m0, U0, P0, tiled=True, leaf_cells=leaf)
+    assert tiled.tile is not None and grid.tile is None
+    for seed in (0, 1):
+        c2, t2, m1 = _coarsened(coords, topo0, ndrop, seed, cuda_device)
+        if case == "ys930_leaf64" and seed == 1:
+            m1.smooth(50)                                               # moved vertices: generic query points
+            c2 = m1.coordinates()
+        Ug, Pg, cg, mg = grid.interpolate(m1)
+        Ut, Pt, ct, mt = tiled.interpolate(m1)
+        assert torch.equal(ct, cg) and int(mt) == int(mg)
+        assert torch.equal(Ut, Ug) and torch.equal(Pt, Pg)
+        topo1 = geom.Topology(t2, len(c2))
+        ref_cells, nmiss, _ = geom.locate(topo1.p2_points(c2), coords, topo0.cells)
+        assert np.array_equal(ct.cpu().numpy(), ref_cells) and int(mt) == nmiss
+    # points outside the mesh (closest-cell fallback) go through the same miss path
+    far = DeviceMesh(np.array([[-0.6, -0.6], [3.2, 0.0], [0.5, 0.7], [1.0, 0.0]]), np.array([[0, 1, 2], [0, 1, 3]]), cuda_device)
+    Ug, Pg, cg, mg = grid.interpolate(far)
+    Ut, Pt, ct, mt = tiled.interpolate(far)
+    assert torch.equal(ct, cg) and int(mt) == int(mg) and int(mt) >= 3
+    assert torch.equal(Ut, Ug) and torch.equal(Pt, Pg)
