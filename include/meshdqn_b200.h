@@ -207,10 +207,15 @@ typedef struct {
     const uint16_t *cvL;        /* [sum nc][6] local dof ids (3 vertices, 3 edges) */
     const uint16_t *binptrL;    /* micro-grid CSR pointers */
     const uint16_t *binsL;      /* micro-grid candidate lists (local cell ids, ascending) */
+    const int32_t *leaf_base;   /* [n_leaves+1] target-record bucket offsets (capacity prefix sums) */
+    int64_t total_cap;          /* = leaf_base[n_leaves] */
 } mdq_tile_index_t;
 
-/* int32 words of workspace mdq_interpolate_tiled needs for np = nv + ne target points */
-int64_t mdq_interp_tiled_workspace_words(const mdq_tile_index_t *idx, int np);
+/* Workspace of mdq_interpolate_tiled, in int32 words:
+ *   counters: persistent, MUST be zero before the first call; every successful call leaves it zeroed again;
+ *   scratch : per call (16-byte aligned), for np = nv + ne target points. */
+int64_t mdq_interp_tiled_counter_words(const mdq_tile_index_t *idx);
+int64_t mdq_interp_tiled_scratch_words(const mdq_tile_index_t *idx, int np);
 /* shared memory (bytes) one CTA of the tiled kernel uses; host-callable */
 int64_t mdq_interp_tiled_smem_bytes(const mdq_tile_index_t *idx);
 
@@ -219,8 +224,8 @@ int64_t mdq_interp_tiled_smem_bytes(const mdq_tile_index_t *idx);
 int mdq_interpolate_tiled(const double *coords, int nv, const int32_t *edges, int ne, const mdq_tile_index_t *idx,
                           const double *coords0, const int32_t *cells0, const int32_t *cell_edges0, int nv0, int ne0,
                           int nc0, const double *U0, const double *P0, double tol, double *U, double *P,
-                          int32_t *cell_of, int32_t *miss_count, int32_t *miss_list, int32_t *workspace,
-                          void *stream);
+                          int32_t *cell_of, int32_t *miss_count, int32_t *miss_list, int32_t *counters,
+                          int32_t *scratch, void *stream);
 
 /* DragProbe/LiftProbe.sample for T <= 8 snapshots (probes.py:23-31,43-50): sum over exterior facets with
  * tag == 1 of |f| (sigma(m_f) n).e_x / e_y.  drag_lift [2][T] f64.  Deterministic fixed-shape reduction. */

@@ -60,11 +60,14 @@ class SourceField:
 
     TILED_MIN_CELLS = 16384   # below this the uniform-grid kernel (one launch) has the lower latency
 
-    def __init__(self, mesh: DeviceMesh, U0, P0, bins_per_cell=4.0, tiled=None, leaf_cells=256, micro_bins_per_cell=4.0):
+    def __init__(self, mesh: DeviceMesh, U0, P0, bins_per_cell=4.0, tiled=None, leaf_cells=None, micro_bins_per_cell=4.0,
+                 bucket_factor=2):
         self.mesh = mesh
         self.tiled = (mesh.nc >= self.TILED_MIN_CELLS) if tiled is None else bool(tiled)
-        self.leaf_cells = int(leaf_cells)
+        self.auto_leaf = leaf_cells is None
+        self.leaf_cells = 128 if leaf_cells is None else int(leaf_cells)
         self.micro_bins_per_cell = float(micro_bins_per_cell)
+        self.bucket_factor = int(bucket_factor)
         self.tile = None
         d = mesh.device
         self.U0 = torch.as_tensor(np.ascontiguousarray(U0, dtype=np.float64)).to(d).contiguous()
@@ -103,24 +106,43 @@ class SourceField:
         """Leaf-packed copy of M0 for the tiled kernel (tile_index.py); built once, M0 never changes (quirk B6)."""
         from .tile_index import build_tile_index
         m, d = self.mesh, self.mesh.device
-        ti = build_tile_index(m.coordinates(), m.cells_host(), m.cell_edges.cpu().numpy(), m.ne,
-                              np.asarray(U0, dtype=np.float64), np.asarray(P0, dtype=np.float64), self.leaf_cells,
-                              bins_per_cell=self.micro_bins_per_cell)
+        L = _lib.lib()
+        k = self.leaf_cells
+        while True:
+            ti = build_tile_index(m.coordinates(), m.cells_host(), m.cell_edges.cpu().numpy(), m.ne,
+                                  np.asarray(U0, dtype=np.float64), np.asarray(P0, dtype=np.float64), k,
+                                  bins_per_cell=self.micro_bins_per_cell, bucket_factor=self.bucket_factor)
+            probe = _lib.mdq_tile_index_t()
+            probe.T = ti.T
+            probe.max_nv, probe.max_np2, probe.max_nc = ti.max_nv, ti.max_np2, ti.max_nc
+            probe.max_nbin, probe.max_nent = ti.max_nbin, ti.max_nent
+            smem = int(L.mdq_interp_tiled_smem_bytes(ctypes.byref(probe)))
+            # the largest leaf sizes every CTA's shared memory: keep two CTAs resident per SM (<= 113 KB each);
+            # an explicit leaf_cells request is honoured as long as one CTA fits at all
+            if smem <= 113 * 1024 or k <= 32 or not self.auto_leaf:
+                break
+            k //= 2
+        self.leaf_cells = k
         self.tile_host = ti
         dev = {k: torch.from_numpy(np.ascontiguousarray(getattr(ti, k))).to(d)
                for k in ("tree", "leaf_info", "leaf_rect", "coordsL", "UL", "PL", "gidL")}
+        dev["leaf_base"] = torch.from_numpy(np.ascontiguousarray(ti.leaf_base, dtype=np.int32)).to(d)
         for k in ("cvL", "binptrL", "binsL"):      # uint16 payloads travel as raw int16 bits
             dev[k] = torch.from_numpy(np.ascontiguousarray(getattr(ti, k)).view(np.int16)).to(d)
         self._tile_dev = dev
         c = _lib.mdq_tile_index_t()
         c.n_leaves, c.depth, c.T = ti.n_leaves, ti.depth, ti.T
         c.max_nv, c.max_np2, c.max_nc, c.max_nbin, c.max_nent = ti.max_nv, ti.max_np2, ti.max_nc, ti.max_nbin, ti.max_nent
-        c.u_stride, c.p_stride = ti.u_stride, ti.p_stride
+        c.u_stride, c.p_stride, c.total_cap = ti.u_stride, ti.p_stride, ti.total_cap
         for k, t in dev.items():
             setattr(c, k, t.data_ptr())
         self.tile = c
         self.tile_bytes = ti.nbytes()
         self.tile_smem = int(_lib.lib().mdq_interp_tiled_smem_bytes(ctypes.byref(c)))
+        # persistent counters (zero on entry, the kernels leave them zeroed) and per-size scratch
+        self._tile_counters = torch.zeros(int(_lib.lib().mdq_interp_tiled_counter_words(ctypes.byref(c))),
+                                          dtype=torch.int32, device=d)
+        self._tile_scratch = None
 
     def interpolate(self, target: DeviceMesh, tol=1e-12):
         """``Function.interpolate`` of every snapshot onto ``target`` (Env2DAirfoil.py:556-568).
@@ -138,13 +160,17 @@ class SourceField:
         L = _lib.lib()
         p = _lib.ptr
         if self.tile is not None:
-            words = int(L.mdq_interp_tiled_workspace_words(ctypes.byref(self.tile), npt))
-            ws = torch.empty(words, dtype=torch.int32, device=d)
+            words = int(L.mdq_interp_tiled_scratch_words(ctypes.byref(self.tile), npt))
+            if self._tile_scratch is None or self._tile_scratch.numel() < words:
+                self._tile_scratch = torch.empty(words, dtype=torch.int32, device=d)
             with torch.cuda.device(d):
                 rc = L.mdq_interpolate_tiled(p(target.coords), target.nv, p(target.edges), target.ne,
                                              ctypes.byref(self.tile), p(m0.coords), p(m0.cells), p(m0.cell_edges), m0.nv,
                                              m0.ne, m0.nc, p(self.U0), p(self.P0), float(tol), p(U), p(P), p(cell_of),
-                                             p(miss), p(miss_list), p(ws), _lib.stream_ptr())
+                                             p(miss), p(miss_list), p(self._tile_counters), p(self._tile_scratch),
+                                             _lib.stream_ptr())
+            if rc != 0:
+                self._tile_counters.zero_()
             _lib.check(rc, "mdq_interpolate_tiled")
             return U, P, cell_of, miss
         with torch.cuda.device(d):

@@ -49,7 +49,7 @@ class mdq_tile_index_t(Structure):
                 ("max_nc", c_int32), ("max_nbin", c_int32), ("max_nent", c_int32), ("u_stride", c_int64),
                 ("p_stride", c_int64), ("tree", c_void_p), ("leaf_info", c_void_p), ("leaf_rect", c_void_p),
                 ("coordsL", c_void_p), ("UL", c_void_p), ("PL", c_void_p), ("gidL", c_void_p), ("cvL", c_void_p),
-                ("binptrL", c_void_p), ("binsL", c_void_p)]
+                ("binptrL", c_void_p), ("binsL", c_void_p), ("leaf_base", c_void_p), ("total_cap", c_int64)]
 
 
 def _newer(src, dst):
@@ -109,10 +109,11 @@ _SIGS = {
     "mdq_grid_fill": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
     "mdq_interpolate": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, POINTER(c_double), _P, _P,
                                 c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mdq_interp_tiled_workspace_words": (c_int64, [POINTER(mdq_tile_index_t), c_int]),
+    "mdq_interp_tiled_counter_words": (c_int64, [POINTER(mdq_tile_index_t)]),
+    "mdq_interp_tiled_scratch_words": (c_int64, [POINTER(mdq_tile_index_t), c_int]),
     "mdq_interp_tiled_smem_bytes": (c_int64, [POINTER(mdq_tile_index_t)]),
     "mdq_interpolate_tiled": (c_int, [_P, c_int, _P, c_int, POINTER(mdq_tile_index_t), _P, _P, _P, c_int, c_int, c_int,
-                                      _P, _P, c_double, _P, _P, _P, _P, _P, _P, _P]),
+                                      _P, _P, c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mdq_drag_lift": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_double, _P, _P]),
     "mdq_build_state": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P,
                                 _P, _P, c_int, _P, _P]),

@@ -23,6 +23,7 @@ a 16-byte boundary and has a 16-byte-multiple size):
   cvL       u16 [sum nc][6]    local dof ids: 3 vertices, 3 edges (index into the leaf's UL rows)
   binptrL   u16 [sum nbin]     micro-grid CSR pointer (gx*gy+1 valid entries)
   binsL     u16 [sum nent]     local cell ids per bin, ascending
+  leaf_base i32 [n_leaves+1]   offsets of the per-leaf target-record buckets (fixed capacities)
 
 A cell belongs to every leaf (and every micro-bin) its bounding box, inflated by `eps`, overlaps, so
 any cell containing a query point to the barycentric tolerance is among the point's candidates and the
@@ -46,7 +47,7 @@ def _pad(n, m):
 class TileIndex:
     __slots__ = ("n_leaves", "depth", "T", "tree", "leaf_info", "leaf_rect", "coordsL", "UL", "PL", "gidL", "cvL",
                  "binptrL", "binsL", "max_nv", "max_np2", "max_nc", "max_nbin", "max_nent", "u_stride", "p_stride",
-                 "leaf_lo", "leaf_hi")
+                 "leaf_lo", "leaf_hi", "leaf_base", "total_cap")
 
     def nbytes(self):
         return sum(getattr(self, k).nbytes for k in ("tree", "leaf_info", "leaf_rect", "coordsL", "UL", "PL", "gidL",
@@ -63,7 +64,8 @@ class TileIndex:
         return node - (self.n_leaves - 1)
 
 
-def build_tile_index(coords, cells, cell_edges, ne, U0, P0, leaf_cells=256, eps=GRID_EPS, bins_per_cell=4.0) -> TileIndex:
+def build_tile_index(coords, cells, cell_edges, ne, U0, P0, leaf_cells=256, eps=GRID_EPS, bins_per_cell=4.0,
+                     bucket_factor=2) -> TileIndex:
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     cells = np.ascontiguousarray(cells, dtype=np.int64)
     cell_edges = np.ascontiguousarray(cell_edges, dtype=np.int64)
@@ -231,6 +233,14 @@ def build_tile_index(coords, cells, cell_edges, ne, U0, P0, leaf_cells=256, eps=
     ti.max_nc, ti.max_nbin, ti.max_nent = int(nc_pad.max()), int(nbin_pad.max()), int(nent_pad.max())
     ti.u_stride, ti.p_stride = int(dbase[-1]), int(vbase[-1])
     ti.leaf_lo, ti.leaf_hi = leaf_lo, leaf_hi
+    # target-record buckets: twice the leaf's own share of M0's P2 points (+ slack); a coarsened or smoothed copy of
+    # M0 never exceeds it, anything denser spills to the kernel's overflow list
+    mid = 0.5 * coords[cells[:, [1, 0, 0]]] + 0.5 * coords[cells[:, [2, 2, 1]]]
+    own = np.bincount(ti.leaf_of(coords), minlength=n_leaves) + \
+        np.bincount(ti.leaf_of(mid.reshape(-1, 2)), minlength=n_leaves) // 2
+    cap = (int(bucket_factor) * own + 32 + 3) // 4 * 4
+    ti.leaf_base = np.concatenate([[0], np.cumsum(cap)]).astype(np.int32)
+    ti.total_cap = int(ti.leaf_base[-1])
     return ti
 
 

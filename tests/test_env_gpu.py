@@ -177,7 +177,7 @@ def _coarsened(coords, cells_topo, n_drop, seed, dev):
     return c2, t2, DeviceMesh(c2, t2, dev)
 
 
-@pytest.mark.parametrize("case", ["ys930_leaf64", "synthetic_leaf256", "synthetic_oversized_leaf"])
+@pytest.mark.parametrize("case", ["ys930_leaf64", "synthetic_leaf256", "synthetic_leaf128_overflow", "synthetic_oversized_leaf"])
 def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, case):
     """The tiled (k-d leaf, TMA-staged) kernel must return the same cell ids and the same field bits as the
     uniform-grid kernel, and the oracle's brute-force cell ids."""
@@ -192,7 +192,7 @@ def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, 
     else:
         coords, cells, _ = synthetic_airfoil_mesh(20000, seed=2)
         topo0 = geom.Topology(cells, len(coords))
-        leaf, ndrop = (256, 150) if case == "synthetic_leaf256" else (8192, 150)
+        leaf, ndrop = {"synthetic_leaf256": (256, 150), "synthetic_leaf128_overflow": (128, 150)}.get(case, (8192, 150))
     U0, P0 = synthetic_fields(coords, topo0.edges, 5, 1)
     m0 = DeviceMesh(coords, cells, cuda_device)
     if case == "synthetic_oversized_leaf":
@@ -200,7 +200,8 @@ def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, 
             SourceField(m0, U0, P0, tiled=True, leaf_cells=leaf).interpolate(m0)
         return
     grid = SourceField(m0, U0, P0, tiled=False)
-    tiled = SourceField(m0, U0, P0, tiled=True, leaf_cells=leaf)
+    # bucket_factor=0: 32-slot buckets, so most points take the overflow path (served from HBM, same bits)
+    tiled = SourceField(m0, U0, P0, tiled=True, leaf_cells=leaf, bucket_factor=0 if case.endswith("overflow") else 2)
     assert tiled.tile is not None and grid.tile is None
     for seed in (0, 1):
         c2, t2, m1 = _coarsened(coords, topo0, ndrop, seed, cuda_device)
@@ -211,6 +212,7 @@ def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, 
         Ut, Pt, ct, mt = tiled.interpolate(m1)
         assert torch.equal(ct, cg) and int(mt) == int(mg)
         assert torch.equal(Ut, Ug) and torch.equal(Pt, Pg)
+        assert int(tiled._tile_counters.abs().sum()) == 0                # counters left zeroed for the next call
         topo1 = geom.Topology(t2, len(c2))
         ref_cells, nmiss, _ = geom.locate(topo1.p2_points(c2), coords, topo0.cells)
         assert np.array_equal(ct.cpu().numpy(), ref_cells) and int(mt) == nmiss

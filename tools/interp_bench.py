@@ -39,7 +39,8 @@ def main():
         alg = 16 * m2.nv + 8 * m2.ne + 16 * m0.nv + 36 * m0.nc + 8 * T * (2 * (m0.nv + m0.ne) + m0.nv) + 8 * T * (2 * npt + m2.nv) + 4 * npt
         print(f"[{order}] mesh {m0.nc} cells, {npt} target points, algorithmic {alg/1e6:.1f} MB, setup {time.time()-t0:.1f}s", flush=True)
         res = {}
-        for name, kw in (("grid", dict(tiled=False)), ("tiled", dict(tiled=True))):
+        leafs = [int(x) for x in os.environ.get("LEAF_CELLS", "256,128").split(",")]
+        for name, kw in [("grid", dict(tiled=False))] + [(f"tiled{k}", dict(tiled=True, leaf_cells=k)) for k in leafs]:
             t0 = time.time()
             src = SourceField(m0, U0, P0, **kw)
             tb = time.time() - t0
@@ -48,21 +49,31 @@ def main():
             res[name] = out
             for _ in range(3):
                 src.interpolate(m2)
-            ts = []
-            for _ in range(10):
-                flush_buf.fill_(1)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                src.interpolate(m2)
-                e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ms = float(np.median(ts))
+            def timed(fn):
+                ts = []
+                for _ in range(10):
+                    flush_buf.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                return float(np.median(ts))
+            ms_eager = timed(lambda: src.interpolate(m2))
+            # CUDA graph of the same call: no host launch latency between the kernels
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gout = src.interpolate(m2)
+            ms = timed(g.replay)
+            assert all(torch.equal(a, b) for a, b in zip(gout[:3], out[:3]))
+            print(f"  {name:9s} eager {ms_eager*1e3:8.1f} us", flush=True)
             extra = f" index {src.tile_bytes/1e6:.1f} MB smem {src.tile_smem} leaves {src.tile_host.n_leaves}" if kw["tiled"] else ""
-            print(f"  {name:6s} build {tb:.2f}s  {ms*1e3:8.1f} us  {alg/ms/1e6:8.1f} GB/s  {alg/ms/1e6/hbm*100:5.1f}% of {hbm:.0f}  "
+            print(f"  {name:9s} build {tb:.2f}s  {ms*1e3:8.1f} us  {alg/ms/1e6:8.1f} GB/s  {alg/ms/1e6/hbm*100:5.1f}% of {hbm:.0f}  "
                   f"{npt/ms/1e6:.2f} Gpts/s  miss {int(out[3])}{extra}", flush=True)
-        same = all(torch.equal(a, b) for a, b in zip(res["grid"][:3], res["tiled"][:3]))
-        print("  tiled == grid bit for bit:", same, flush=True)
+        for k in res:
+            if k != "grid":
+                print(f"  {k} == grid bit for bit:", all(torch.equal(a, b) for a, b in zip(res["grid"][:3], res[k][:3])), flush=True)
 
 
 if __name__ == "__main__":
