@@ -114,6 +114,37 @@ int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const fl
                              const int32_t *index, const int32_t *next_slot, const float *q_other, int batch, float gamma,
                              float *scalar, float *loss, float *grad, float *workspace, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Layered forward for ONE large graph (a state graph that does not fit the fused kernel's shared memory, e.g. the
+ * ~0.5M-node graph of a ~1M-triangle mesh).  Same network, same results (to fp32 rounding) as mdq_qnet_forward:
+ * CSR message passing (warp per row), node GEMMs, radix-sort TopK, ordered edge filter, readout, MLP head.
+ *   gemm_mode 0: fp32 FFMA node GEMMs;  1: tcgen05 3xTF32 (tensor cores, TMEM accumulator; conv width 128).
+ *   wsplit (gemm_mode 1): 3 * n_params floats; the conv weight at w_off is stored at 3 * w_off as
+ *     hi [Kpad/4][16][8][4] then lo (same shape), Kpad = K rounded up to 8, hi = w & 0xffffe000, lo = w - hi,
+ *     element [c][g][r][kk] = W[4c+kk][8g+r]  (K-major core matrices of the UMMA canonical layout).
+ * ------------------------------------------------------------------------------------ */
+int64_t mdq_qnet_layered_workspace_bytes(const mdq_net_t *net, int n_nodes, int n_edges);
+int mdq_qnet_forward_layered(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
+                             const int64_t *edge_src, const int64_t *edge_dst, int n_nodes, int n_edges, int gemm_mode,
+                             float *out, float *embedding, int32_t *argmax, void *workspace, int64_t workspace_bytes,
+                             void *stream);
+
+/* Building blocks of the layered path, exported for parity tests and roofline measurement.
+ * mdq_csr_build: CSR by destination with rows in edge order; ecount is a DEVICE int (<= ecap);
+ *   scratch: mdq_csr_build_scratch_words(ecap, n) int32 words.
+ * mdq_sage_aggregate (torch_geometric SAGEConv message passing, airfoilgcnn.py:94,100):
+ *   A[i] = [ mean_{j->i} x[j, col0:col0+F] | x[i, col0:col0+F] | 0 ... ] with row stride lda >= 2F.
+ * mdq_node_gemm: C[M,N] = epilogue(A[rows][K] . W[K][N]): + bias, ReLU, score[m] = tanh(h.pool/||pool||),
+ *   stored row scaled by row_scale[source row]; every pointer after W may be NULL. */
+int mdq_csr_build(const int32_t *src, const int32_t *dst, const int32_t *ecount, int ecap, int n, int32_t *row_ptr,
+                  int32_t *col, int32_t *scratch, void *stream);
+int64_t mdq_csr_build_scratch_words(int ecap, int n);
+int mdq_sage_aggregate(const float *x, int ldx, int col0, int F, const int32_t *row_ptr, const int32_t *col, int n,
+                       float *A, int lda, void *stream);
+int mdq_node_gemm(const float *A, const int32_t *rows, int lda, int K, int M, int N, const float *W, const float *wsplit,
+                  const float *bias, const float *pool, const float *row_scale, int relu, int gemm_mode, float *C,
+                  float *score, void *stream);
+
 /* Replay-minibatch loss (replaces /root/reference/airfoil_dqn.py:264,267-283,303-304):
  *   pred_b = q1[b, action[b]];  target_b = reward[b] + gamma * (nonfinal[b] ? max_a q2[slot[b], a] : 0)
  *   loss = mean_b huber(pred_b - target_b, delta = 1)

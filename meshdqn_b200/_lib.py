@@ -23,6 +23,7 @@ _OBJ = os.path.join(_HERE, "csrc", "_obj")
 _SOURCES = (
     ("common.cu", ()),
     ("gnn_fused.cu", ()),
+    ("gnn_layered.cu", ()),
     ("geom.cu", ("-fmad=false",)),
 )
 _NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -98,6 +99,12 @@ _SIGS = {
     "mdq_qnet_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mdq_qnet_replay_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
                                          _P, c_int, c_float, _P, _P, _P, _P, _P]),
+    "mdq_qnet_layered_workspace_bytes": (c_int64, [POINTER(mdq_net_t), c_int, c_int]),
+    "mdq_qnet_forward_layered": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "mdq_csr_build": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "mdq_csr_build_scratch_words": (c_int64, [c_int, c_int]),
+    "mdq_sage_aggregate": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
+    "mdq_node_gemm": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "mdq_huber_replay": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P]),
     "mdq_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "mdq_scan_i32": (c_int, [_P, _P, c_int, _P]),

@@ -337,9 +337,71 @@ class _FusedQNet(nn.Module):
                                             _lib.stream_ptr())
         _lib.check(rc, "mdq_qnet_replay_backward")
 
+    # -- layered path: one large graph (does not fit a CTA's shared memory) -----------------------------------
+    FUSED_MAX_NODES = 2048          # above this a single graph goes layer by layer (gnn_layered.cu)
+    layered_gemm = "tf32x3"         # "tf32x3": tcgen05 tensor cores (3xTF32, ~fp32 accuracy) | "fp32": FFMA
+
+    def _pack_wsplit(self):
+        """hi/lo TF32 split of the conv weights, tiled as K-major UMMA core matrices (include/meshdqn_b200.h)."""
+        net, flat = self._net, self._flat
+        ws = torch.zeros(3 * net.n_params, dtype=torch.float32, device=flat.device)
+        W = net.width
+        for bi in range(net.n_blocks):
+            b = net.blk[bi]
+            K = 2 * b.kin if b.type == MDQ_BLOCK_SAGE else b.kin
+            kpad = (K + 7) // 8 * 8
+            w = torch.zeros(kpad, W, dtype=torch.float32, device=flat.device)
+            w[:K] = flat[b.w_off:b.w_off + K * W].view(K, W)
+            hi = (w.view(torch.int32) & -8192).view(torch.float32)          # 0xffffe000
+            lo = w - hi
+
+            def tile(m):   # [kpad][W] -> [kpad/4][W/8][8][4], element [c][g][r][kk] = m[4c+kk][8g+r]
+                return m.view(kpad // 4, 4, W // 8, 8).permute(0, 2, 3, 1).contiguous().view(-1)
+            o = 3 * b.w_off
+            ws[o:o + kpad * W] = tile(hi)
+            ws[o + kpad * W:o + 2 * kpad * W] = tile(lo)
+        self._wsplit = ws
+        self._wsplit_version = self._flat._version
+
+    def _launch_forward_layered(self, x, ei, embedding, want_argmax):
+        self._ensure_packed()
+        net = self._net
+        net.x_stride = int(x.shape[1])
+        N, E = int(x.shape[0]), int(ei.shape[1])
+        mode = 1 if (self.layered_gemm == "tf32x3" and net.width == 128) else 0
+        if mode == 1 and (getattr(self, "_wsplit", None) is None or self._wsplit.device != x.device
+                          or self._wsplit_version != self._flat._version):
+            self._pack_wsplit()
+        L = _lib.lib()
+        need = int(L.mdq_qnet_layered_workspace_bytes(net, N, E))
+        if need < 0:
+            raise RuntimeError("mdq_qnet_layered_workspace_bytes failed")
+        lw = getattr(self, "_layered_ws", None)
+        if lw is None or lw.numel() < need or lw.device != x.device:
+            self._layered_ws = lw = torch.empty(need, dtype=torch.uint8, device=x.device)
+        out = torch.empty((1, net.out_dim), dtype=torch.float32, device=x.device)
+        emb = torch.empty((1, 2 * net.width), dtype=torch.float32, device=x.device) if embedding else None
+        am = torch.empty((1,), dtype=torch.int32, device=x.device) if want_argmax else None
+        with torch.cuda.device(x.device):
+            rc = L.mdq_qnet_forward_layered(net, _lib.ptr(self._flat), _lib.ptr(self._wsplit if mode == 1 else None),
+                                            _lib.ptr(x), _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+                                            N, E, mode, _lib.ptr(out), _lib.ptr(emb), _lib.ptr(am), _lib.ptr(lw), need,
+                                            _lib.stream_ptr())
+        _lib.check(rc, "mdq_qnet_forward_layered")
+        return out, emb, am
+
+    def _use_layered(self, B, max_n):
+        return B == 1 and max_n > self.FUSED_MAX_NODES
+
     def _forward_impl(self, data, embedding=False):
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
         self._ensure_packed()
+        if self._use_layered(B, max_n):
+            if torch.is_grad_enabled() and any(p.requires_grad for _, p in self._entries):
+                raise NotImplementedError("the layered large-graph path is forward-only (Q-evaluation); wrap the call in "
+                                          "torch.no_grad()")
+            out, emb, _ = self._launch_forward_layered(x, ei, embedding, False)
+            return emb if embedding else out
         params = [p for _, p in self._entries]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _QNetFunction.apply(self, x, ei, nptr, eptr, B, max_n, max_e, embedding, *params)
@@ -350,6 +412,9 @@ class _FusedQNet(nn.Module):
     def select_action(self, data):
         """Fused softmax + argmax (airfoil_dqn.py:208-209): returns (action i32 [B], q [B, A])."""
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
+        if self._use_layered(B, max_n):
+            out, _, am = self._launch_forward_layered(x, ei, False, True)
+            return am, out
         out, _, am = self._launch_forward(x, ei, nptr, eptr, B, max_n, max_e, False, True)
         return am, out
 
