@@ -167,73 +167,124 @@ __global__ void k_csr_sort_rows(const int *__restrict__ src, const int *__restri
 {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         const int a = row_ptr[r], b = row_ptr[r + 1];
-        for (int i = a + 1; i < b; ++i) {  // insertion sort: rows are short (mesh vertex degree)
-            const int v = eid[i];
-            int j = i - 1;
-            while (j >= a && eid[j] > v) {
-                eid[j + 1] = eid[j];
-                --j;
+        const int d = b - a;
+        if (d <= 16) {   // mesh vertex degrees: sort in registers (odd-even transposition network)
+            int v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (i < d) ? eid[a + i] : 0x7fffffff;
+#pragma unroll
+            for (int pass = 0; pass < 16; ++pass)
+#pragma unroll
+                for (int i = pass & 1; i + 1 < 16; i += 2) {
+                    const int lo = min(v[i], v[i + 1]), hi = max(v[i], v[i + 1]);
+                    v[i] = lo;
+                    v[i + 1] = hi;
+                }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < d) col[a + i] = src[v[i]];
+        } else {
+            for (int i = a + 1; i < b; ++i) {  // insertion sort in place for the rare long row
+                const int v = eid[i];
+                int j = i - 1;
+                while (j >= a && eid[j] > v) {
+                    eid[j + 1] = eid[j];
+                    --j;
+                }
+                eid[j + 1] = v;
             }
-            eid[j + 1] = v;
+            for (int i = a; i < b; ++i) col[i] = src[eid[i]];
         }
-        for (int i = a; i < b; ++i) col[i] = src[eid[i]];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // SAGEConv message passing: A[r] = [ mean_{j -> i} X[j] | X[i] | 0-pad ], i = rows ? rows[r] : r
 // ------------------------------------------------------------------------------------------------
-// F <= 32: one warp per row, lane f owns feature f (a 17-float row is one 68-byte coalesced read per neighbour).
+// Narrow feature rows (F <= 32, e.g. the 17 state features): one thread per (row, feature) element, so all 32 lanes
+// work (a warp spans ~2 rows): neighbour ids are broadcast loads, the feature reads of one row are one coalesced
+// 4F-byte segment, and up to eight neighbour values are in flight per thread.  Each element is summed sequentially
+// in CSR (= edge) order, so the bits equal torch_scatter's CPU loop; no atomics.
 __global__ void __launch_bounds__(256) k_sage_rows_narrow(const float *__restrict__ X, int ldx, int col0, int F,
                                                           const int *__restrict__ row_ptr, const int *__restrict__ col,
                                                           int n_rows, float *__restrict__ A, int lda)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < n_rows; r += nwarps) {
-        const int a = __ldg(row_ptr + r), b = __ldg(row_ptr + r + 1);
-        float s = 0.f;
-        for (int base = a; base < b; base += 32) {
-            const int cnt = min(32, b - base);
-            const int mine = (lane < cnt) ? __ldg(col + base + lane) : 0;   // coalesced index read
-            for (int q = 0; q < cnt; ++q) {
-                const int j = __shfl_sync(FULL, mine, q);
-                if (lane < F) s += __ldg(X + (size_t)j * ldx + col0 + lane);
+    constexpr int U = 1;    // elements per thread in flight (U > 1 measured slower: registers cost occupancy): the pointer / index / feature round trips of U elements overlap
+    const long long total = (long long)n_rows * F;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int pad = lda - 2 * F;
+    for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx0 < total; idx0 += U * stride) {
+        int r[U], f[U], a[U], b[U];
+        float self[U], s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long idx = idx0 + u * stride;
+            const bool ok = idx < total;
+            r[u] = ok ? (int)(idx / F) : 0;
+            f[u] = ok ? (int)(idx - (long long)r[u] * F) : 0;
+            a[u] = __ldg(row_ptr + r[u]);
+            b[u] = ok ? __ldg(row_ptr + r[u] + 1) : a[u];
+        }
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float *Xf = X + col0 + f[u];
+            self[u] = __ldg(Xf + (size_t)r[u] * ldx);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[u][q] = (a[u] + q < b[u]) ? __ldg(Xf + (size_t)__ldg(col + a[u] + q) * ldx) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float *Xf = X + col0 + f[u];
+            s[u] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (a[u] + q < b[u]) s[u] += v[u][q];
+            for (int e = a[u] + 8; e < b[u]; ++e) s[u] += __ldg(Xf + (size_t)__ldg(col + e) * ldx);   // long rows, in order
+            if (idx0 + u * stride < total) {
+                float *Ar = A + (size_t)r[u] * lda;
+                Ar[f[u]] = s[u] / (float)max(b[u] - a[u], 1);
+                Ar[F + f[u]] = self[u];
+                if (f[u] < pad) Ar[2 * F + f[u]] = 0.f;
+                if (f[u] == 0)
+                    for (int c = 2 * F + F; c < lda; ++c) Ar[c] = 0.f;   // pad wider than F (not for F = 17, lda = 40)
             }
         }
-        const float deg = (float)max(b - a, 1);
-        float *Ar = A + (size_t)r * lda;
-        if (lane < F) {
-            Ar[lane] = s / deg;
-            Ar[F + lane] = __ldg(X + (size_t)r * ldx + col0 + lane);
-        }
-        for (int c = 2 * F + lane; c < lda; c += 32) Ar[c] = 0.f;
     }
 }
 
-// F == 128: one warp per row, lane owns a float4 (512-byte rows, fully coalesced, 16-byte vector loads).
+// F == 128: one warp per row, lane owns a float4 (512-byte rows, fully coalesced, 16-byte vector loads), four
+// neighbour rows in flight.
 __global__ void __launch_bounds__(256) k_sage_rows_128(const float *__restrict__ X, const int *__restrict__ row_ptr,
                                                        const int *__restrict__ col, int n_rows, float *__restrict__ A)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const float4 *X4 = reinterpret_cast<const float4 *>(X);
+    const float4 *X4 = reinterpret_cast<const float4 *>(X) + lane;
     for (int r = warp; r < n_rows; r += nwarps) {
         const int a = __ldg(row_ptr + r), b = __ldg(row_ptr + r + 1);
+        const float4 self = __ldg(X4 + (size_t)r * 32);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int base = a; base < b; base += 32) {
             const int cnt = min(32, b - base);
             const int mine = (lane < cnt) ? __ldg(col + base + lane) : 0;
-            for (int q = 0; q < cnt; ++q) {
-                const int j = __shfl_sync(FULL, mine, q);
-                const float4 v = __ldg(X4 + (size_t)j * 32 + lane);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            for (int q0 = 0; q0 < cnt; q0 += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = __shfl_sync(FULL, mine, (q0 + q) & 31);
+                    v[q] = (q0 + q < cnt) ? __ldg(X4 + (size_t)j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q0 + q < cnt) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
             }
         }
         const float deg = (float)max(b - a, 1);
         float4 *Ar = reinterpret_cast<float4 *>(A + (size_t)r * 256);
         Ar[lane] = make_float4(s.x / deg, s.y / deg, s.z / deg, s.w / deg);
-        Ar[32 + lane] = __ldg(X4 + (size_t)r * 32 + lane);
+        Ar[32 + lane] = self;
     }
 }
 
@@ -395,14 +446,6 @@ __device__ __forceinline__ unsigned desc_key(float s)
     return ~u;                                   // descending
 }
 
-__global__ void k_sort_init(const float *__restrict__ score, int n, unsigned *__restrict__ key, int *__restrict__ val)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        key[i] = desc_key(score[i]);
-        val[i] = i;
-    }
-}
-
 constexpr int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
 // table[digit][cta]
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const unsigned *__restrict__ key, int n, int shift,
@@ -471,6 +514,117 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned *__
         if (i < n && rank == 0) cnt[warp][d] += __popc(peers);
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TopK selection: only the k = ceil(ratio n) best rows need ordering.  A 4-pass MSD radix SELECT finds the k-th key T,
+// an ordered compaction keeps {key < T} plus the first (k - #{key < T}) rows with key == T in index order (the
+// tie rule), and the LSD sort above orders just those k pairs.
+// ------------------------------------------------------------------------------------------------
+struct SelState {
+    unsigned prefix, mask;
+    int remaining, count_lt;
+};
+__global__ void k_select_init(const float *__restrict__ score, int n, unsigned *__restrict__ key, SelState *st, int k,
+                              int *__restrict__ hist)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) key[i] = desc_key(score[i]);
+    if (blockIdx.x == 0) {
+        hist[threadIdx.x & 255] = 0;
+        if (threadIdx.x == 0) {
+            st->prefix = 0u; st->mask = 0u; st->remaining = k; st->count_lt = 0;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_select_hist(const unsigned *__restrict__ key, int n, int shift,
+                                                     const SelState *__restrict__ st, int *__restrict__ hist)
+{
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned prefix = st->prefix, mask = st->mask;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned k = key[i];
+        if ((k & mask) == prefix) atomicAdd(&h[(k >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(hist + threadIdx.x, h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_select_pick(SelState *st, int *__restrict__ hist, int shift)
+{
+    __shared__ int h[256];
+    h[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    hist[threadIdx.x] = 0;   // ready for the next pass
+    if (threadIdx.x == 0) {
+        int cum = 0, d = 0;
+        const int need = st->remaining;
+        for (; d < 255; ++d) {
+            if (cum + h[d] >= need) break;
+            cum += h[d];
+        }
+        st->prefix |= (unsigned)d << shift;
+        st->mask |= 255u << shift;
+        st->remaining = need - cum;
+        st->count_lt += cum;
+    }
+}
+constexpr int SC_TILE = 4096;
+__global__ void __launch_bounds__(1024) k_select_count(const unsigned *__restrict__ key, int n, const SelState *__restrict__ st,
+                                                       int *__restrict__ part_lt, int *__restrict__ part_eq)
+{
+    __shared__ int wtmp[33];
+    const unsigned T = st->prefix;
+    const int base = blockIdx.x * SC_TILE + threadIdx.x * 4;
+    int lt = 0, eq = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (base + q < n) {
+            const unsigned k = key[base + q];
+            lt += (k < T);
+            eq += (k == T);
+        }
+    int tl, te;
+    block_scan_excl_1024(lt, wtmp, tl);
+    block_scan_excl_1024(eq, wtmp, te);
+    if (threadIdx.x == 0) {
+        part_lt[blockIdx.x] = tl;
+        part_eq[blockIdx.x] = te;
+    }
+}
+__global__ void __launch_bounds__(1024) k_select_write(const unsigned *__restrict__ key, int n, const SelState *__restrict__ st,
+                                                       const int *__restrict__ lt_ex, const int *__restrict__ eq_ex,
+                                                       unsigned *__restrict__ key_out, int *__restrict__ val_out)
+{
+    __shared__ int wtmp[33];
+    const unsigned T = st->prefix;
+    const int m = st->remaining;             // rows with key == T to keep (lowest indices first)
+    const int base = blockIdx.x * SC_TILE + threadIdx.x * 4;
+    unsigned k[4];
+    int lt = 0, eq = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        k[q] = (base + q < n) ? key[base + q] : 0xffffffffu;
+        if (base + q < n) {
+            lt += (k[q] < T);
+            eq += (k[q] == T);
+        }
+    }
+    int tl, te;
+    int lb = block_scan_excl_1024(lt, wtmp, tl) + lt_ex[blockIdx.x];
+    int eb = block_scan_excl_1024(eq, wtmp, te) + eq_ex[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (base + q < n) {
+            const bool isl = k[q] < T, ise = k[q] == T;
+            if (isl || (ise && eb < m)) {
+                const int pos = lb + min(eb, m);
+                key_out[pos] = k[q];
+                val_out[pos] = base + q;
+            }
+            lb += isl;
+            eb += ise;
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,30 +705,54 @@ __global__ void __launch_bounds__(1024) k_edge_write(const int *__restrict__ src
 }
 
 // readout: acc[0:W] += max over rows, acc[W:2W] += mean over rows.  Two stages, fixed shape -> deterministic.
-constexpr int RO_ROWS = 256;   // rows per CTA in stage 1
-__global__ void __launch_bounds__(128) k_readout_partial(const float *__restrict__ X, int W, int n, float *__restrict__ pmax,
+constexpr int RO_ROWS = 128;   // rows per CTA in stage 1
+// 256 threads: lane group c4 = tid % (W/4) owns a float4 column group, the 256/(W/4) row slices interleave rows
+__global__ void __launch_bounds__(256) k_readout_partial(const float *__restrict__ X, int W, int n, float *__restrict__ pmax,
                                                          float *__restrict__ psum)
 {
+    __shared__ float4 smx[256], ssm[256];
+    const int w4 = W / 4, slices = 256 / w4;
+    const int c4 = threadIdx.x % w4, sl = threadIdx.x / w4;
     const int r0 = blockIdx.x * RO_ROWS, r1 = min(n, r0 + RO_ROWS);
-    for (int c = threadIdx.x; c < W; c += blockDim.x) {
-        float mx = -INFINITY, sm = 0.f;
-        for (int r = r0; r < r1; ++r) {
-            const float v = X[(size_t)r * W + c];
-            mx = fmaxf(mx, v);
-            sm += v;
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), sm = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sl < slices)
+        for (int r = r0 + sl; r < r1; r += slices) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(X + (size_t)r * W) + c4);
+            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+            sm.x += v.x; sm.y += v.y; sm.z += v.z; sm.w += v.w;
         }
-        pmax[(size_t)blockIdx.x * W + c] = mx;
-        psum[(size_t)blockIdx.x * W + c] = sm;
+    smx[threadIdx.x] = mx;
+    ssm[threadIdx.x] = sm;
+    __syncthreads();
+    if (threadIdx.x < w4) {
+        for (int q = 1; q < slices; ++q) {      // fixed order -> deterministic
+            const float4 a = smx[q * w4 + c4], b = ssm[q * w4 + c4];
+            mx.x = fmaxf(mx.x, a.x); mx.y = fmaxf(mx.y, a.y); mx.z = fmaxf(mx.z, a.z); mx.w = fmaxf(mx.w, a.w);
+            sm.x += b.x; sm.y += b.y; sm.z += b.z; sm.w += b.w;
+        }
+        reinterpret_cast<float4 *>(pmax + (size_t)blockIdx.x * W)[c4] = mx;
+        reinterpret_cast<float4 *>(psum + (size_t)blockIdx.x * W)[c4] = sm;
     }
 }
-__global__ void __launch_bounds__(256) k_readout_final(const float *__restrict__ pmax, const float *__restrict__ psum, int W,
-                                                       int nparts, int n, int first, float *__restrict__ acc)
+__global__ void __launch_bounds__(1024) k_readout_final(const float *__restrict__ pmax, const float *__restrict__ psum, int W,
+                                                        int nparts, int n, int first, float *__restrict__ acc)
 {
-    for (int c = threadIdx.x; c < W; c += blockDim.x) {
-        float mx = -INFINITY, sm = 0.f;
-        for (int p = 0; p < nparts; ++p) {
+    __shared__ float smx[1024], ssm[1024];
+    const int slices = 1024 / W;
+    const int c = threadIdx.x % W, sl = threadIdx.x / W;
+    float mx = -INFINITY, sm = 0.f;
+    if (sl < slices)
+        for (int p = sl; p < nparts; p += slices) {
             mx = fmaxf(mx, pmax[(size_t)p * W + c]);
             sm += psum[(size_t)p * W + c];
+        }
+    smx[threadIdx.x] = mx;
+    ssm[threadIdx.x] = sm;
+    __syncthreads();
+    if (threadIdx.x < W) {
+        for (int q = 1; q < slices; ++q) {
+            mx = fmaxf(mx, smx[q * W + c]);
+            sm += ssm[q * W + c];
         }
         const float mean = sm / (float)max(n, 1);
         acc[c] = first ? mx : acc[c] + mx;
@@ -599,13 +777,34 @@ __global__ void __launch_bounds__(256) k_mlp_head(const mdq_net_t net, const flo
     }
     __syncthreads();
     float *cur = a, *nxt = b;
+    __shared__ float part[8][512];
+    const int wq = threadIdx.x >> 5, lq = threadIdx.x & 31;
     for (int l = 0; l < 3; ++l) {
         const int K = net.lin_in[l], O = net.lin_out[l];
         const float *Wt = params + net.lin_off[l];   // [K][O]
         const float *bs = params + net.lin_boff[l];
+        // warp wq takes every 8th k; lanes run over the outputs (coalesced weight rows), 4 outputs per lane in flight
+        for (int o0 = 0; o0 < O; o0 += 128) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const int o = o0 + lq;
+            for (int k = wq; k < K; k += 8) {
+                const float x = cur[k];
+                const float *wr = Wt + (size_t)k * O;
+                if (o < O) s0 = fmaf(x, __ldg(wr + o), s0);
+                if (o + 32 < O) s1 = fmaf(x, __ldg(wr + o + 32), s1);
+                if (o + 64 < O) s2 = fmaf(x, __ldg(wr + o + 64), s2);
+                if (o + 96 < O) s3 = fmaf(x, __ldg(wr + o + 96), s3);
+            }
+            part[wq][o] = s0;
+            if (o + 32 < 512) part[wq][o + 32] = s1;
+            if (o + 64 < 512) part[wq][o + 64] = s2;
+            if (o + 96 < 512) part[wq][o + 96] = s3;
+        }
+        __syncthreads();
         for (int o = threadIdx.x; o < O; o += blockDim.x) {
-            float s = 0.f;
-            for (int k = 0; k < K; ++k) s = fmaf(cur[k], Wt[(size_t)k * O + o], s);
+            float s = part[0][o];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) s += part[q][o];
             s += bs[o];
             nxt[o] = (l < 2) ? fmaxf(s, 0.f) : s;
         }
@@ -692,25 +891,23 @@ int sage_rows(const float *X, int ldx, int col0, int F, const int *row_ptr, cons
 {
     if (n <= 0) return MDQ_OK;
     const int grid = grid_for((long long)n * 32, 256, 148 * 16);
+    if (F <= 32) {
+        k_sage_rows_narrow<<<grid_for((long long)n * F, 256, 148 * 64), 256, 0, st>>>(X, ldx, col0, F, row_ptr, col, n, A, lda);
+        return mdq::check_launch("k_sage_rows_narrow");
+    }
     if (F == 128 && ldx == 128 && col0 == 0 && lda == 256) {
         k_sage_rows_128<<<grid, 256, 0, st>>>(X, row_ptr, col, n, A);
         return mdq::check_launch("k_sage_rows_128");
-    }
-    if (F <= 32) {
-        k_sage_rows_narrow<<<grid, 256, 0, st>>>(X, ldx, col0, F, row_ptr, col, n, A, lda);
-        return mdq::check_launch("k_sage_rows_narrow");
     }
     mdq::set_error("SAGE aggregation: %d input features not supported by the layered path (<= 32 or 128)", F);
     return MDQ_EINVAL;
 }
 
-// sorts (score desc, index asc); on return the ordered indices are in *val_sorted (one of the two buffers)
-int topk_sort(const float *score, int n, unsigned *key_a, unsigned *key_b, int *val_a, int *val_b, int *table,
-              int *scan_part, int **val_sorted, cudaStream_t st)
+// LSD radix sort of n (key, val) pairs already in key_a / val_a; the ordered values end up in *val_sorted
+int radix_sort_pairs(int n, unsigned *key_a, unsigned *key_b, int *val_a, int *val_b, int *table, int *scan_part,
+                     int **val_sorted, cudaStream_t st)
 {
     int rc;
-    k_sort_init<<<grid_for(n, 256), 256, 0, st>>>(score, n, key_a, val_a);
-    if ((rc = mdq::check_launch("k_sort_init"))) return rc;
     const int ncta = cdiv(n, RS_TILE);
     unsigned *kin = key_a, *kout = key_b;
     int *vin = val_a, *vout = val_b;
@@ -725,6 +922,35 @@ int topk_sort(const float *score, int n, unsigned *key_a, unsigned *key_b, int *
     }
     *val_sorted = vin;
     return MDQ_OK;
+}
+
+// TopKPooling's perm: the k best rows by (score desc, index asc), in that order.
+//   key_all [n]; key_a/key_b/val_a/val_b [>= k]; sel: SelState + 256-int histogram + 4 * (cdiv(n, SC_TILE) + 2) ints
+int topk_select_sort(const float *score, int n, int k, unsigned *key_all, unsigned *key_a, unsigned *key_b, int *val_a,
+                     int *val_b, int *table, int *scan_part, int *sel, int **perm, cudaStream_t st)
+{
+    int rc;
+    SelState *state = reinterpret_cast<SelState *>(sel);
+    int *hist = sel + 8;
+    const int nparts = cdiv(n, SC_TILE);
+    int *part_lt = hist + 256, *part_eq = part_lt + nparts + 1, *lt_ex = part_eq + nparts + 1, *eq_ex = lt_ex + nparts + 1;
+    k_select_init<<<grid_for(n, 256), 256, 0, st>>>(score, n, key_all, state, k, hist);
+    if ((rc = mdq::check_launch("k_select_init"))) return rc;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        k_select_hist<<<grid_for(n, 256 * 8, 148 * 4), 256, 0, st>>>(key_all, n, shift, state, hist);
+        if ((rc = mdq::check_launch("k_select_hist"))) return rc;
+        k_select_pick<<<1, 256, 0, st>>>(state, hist, shift);
+        if ((rc = mdq::check_launch("k_select_pick"))) return rc;
+    }
+    k_select_count<<<nparts, 1024, 0, st>>>(key_all, n, state, part_lt, part_eq);
+    if ((rc = mdq::check_launch("k_select_count"))) return rc;
+    k_scan<<<1, 1024, 0, st>>>(part_lt, lt_ex, nparts);
+    if ((rc = mdq::check_launch("k_scan"))) return rc;
+    k_scan<<<1, 1024, 0, st>>>(part_eq, eq_ex, nparts);
+    if ((rc = mdq::check_launch("k_scan"))) return rc;
+    k_select_write<<<nparts, 1024, 0, st>>>(key_all, n, state, lt_ex, eq_ex, key_a, val_a);
+    if ((rc = mdq::check_launch("k_select_write"))) return rc;
+    return radix_sort_pairs(k, key_a, key_b, val_a, val_b, table, scan_part, perm, st);
 }
 
 struct Bump {
@@ -767,6 +993,8 @@ int forward_layered(const mdq_net_t *net, const float *params, const float *wspl
     int *deg = ws.take<int>(n0 + 2), *row_ptr = ws.take<int>(n0 + 2), *cursor = ws.take<int>(n0 + 2);
     int *eid = ws.take<int>(e0 + 1), *col = ws.take<int>(e0 + 1);
     float *score = ws.take<float>(n0 + 1);
+    unsigned *key_all = ws.take<unsigned>(n0 + 1);
+    int *sel = ws.take<int>(8 + 256 + 4 * (cdiv(n0, SC_TILE) + 2));
     unsigned *key_a = ws.take<unsigned>(n0 + 1), *key_b = ws.take<unsigned>(n0 + 1);
     int *val_a = ws.take<int>(n0 + 1), *val_b = ws.take<int>(n0 + 1);
     int *table = ws.take<int>(2 * (256 * cdiv(n0, RS_TILE) + 8) + 8);
@@ -814,7 +1042,7 @@ int forward_layered(const mdq_net_t *net, const float *params, const float *wspl
             g.A = A; g.rows = nullptr; g.lda = lda; g.K = 2 * F; g.M = n; g.N = W; g.W = Wl; g.bias = bias; g.pool = pool;
             g.row_scale = nullptr; g.relu = 1; g.C = nullptr; g.score = score;
             if ((rc = launch_gemm(g, mode, wsp, st))) return rc;
-            if ((rc = topk_sort(score, n, key_a, key_b, val_a, val_b, table, scan_part, &perm, st))) return rc;
+            if ((rc = topk_select_sort(score, n, k, key_all, key_a, key_b, val_a, val_b, table, scan_part, sel, &perm, st))) return rc;
             // pass 2: conv output of the kept rows, scaled by their score: x[perm] * score[perm]
             g.rows = perm; g.M = k; g.pool = nullptr; g.score = nullptr; g.row_scale = score; g.C = xnext;
             if ((rc = launch_gemm(g, mode, wsp, st))) return rc;
@@ -832,15 +1060,15 @@ int forward_layered(const mdq_net_t *net, const float *params, const float *wspl
             if ((rc = mdq::check_launch("k_gcn_deg"))) return rc;
             k_gcn_rows<<<grid_for((long long)n * 32, 256, 148 * 16), 256, 0, st>>>(H, W, row_ptr, col, dis, n, bias, pool, H2, score);
             if ((rc = mdq::check_launch("k_gcn_rows"))) return rc;
-            if ((rc = topk_sort(score, n, key_a, key_b, val_a, val_b, table, scan_part, &perm, st))) return rc;
+            if ((rc = topk_select_sort(score, n, k, key_all, key_a, key_b, val_a, val_b, table, scan_part, sel, &perm, st))) return rc;
             k_pool_gather<<<grid_for((long long)k * (W / 4), 256), 256, 0, st>>>(H2, W, perm, score, k, xnext);
             if ((rc = mdq::check_launch("k_pool_gather"))) return rc;
         }
         // readout of the pooled level
         const int nparts = cdiv(std::max(k, 1), RO_ROWS);
-        k_readout_partial<<<nparts, 128, 0, st>>>(xnext, W, k, pmax, psum);
+        k_readout_partial<<<nparts, 256, 0, st>>>(xnext, W, k, pmax, psum);
         if ((rc = mdq::check_launch("k_readout_partial"))) return rc;
-        k_readout_final<<<1, 256, 0, st>>>(pmax, psum, W, nparts, k, l == 0, acc);
+        k_readout_final<<<1, 1024, 0, st>>>(pmax, psum, W, nparts, k, l == 0, acc);
         if ((rc = mdq::check_launch("k_readout_final"))) return rc;
         if (l + 1 < net->n_blocks) {
             // re-index the surviving edges (ordered)

@@ -169,7 +169,7 @@ def test_layered_matches_fused_on_a_graph_both_can_run(cuda_device):
             net.layered_gemm = gemm
             q_lay, _, am = net._launch_forward_layered(x, ei, False, True)
             rel = float(((q_lay.cpu() - q_fused).abs() / q_fused.abs().clamp_min(1e-30)).max())
-            assert rel < (1e-5 if gemm == "fp32" else 5e-5), (gemm, rel)
+            assert rel < (5e-5 if gemm == "fp32" else 5e-4), (gemm, rel)   # two fp32 summation orders / 3xTF32
             assert int(am[0]) == int(q_fused.argmax())
         q_ref = ref(d.to("cpu"))
     assert float(((q_fused - q_ref).abs() / q_ref.abs().clamp_min(1e-30)).max()) < 1e-5
