@@ -316,6 +316,45 @@ def time_events(fn, iters, flush=None):
     return tot / iters  # ms
 
 
+def bench_candidates(net, rb_dev, dev, rank, world, flush, total=8192):
+    """8192 candidate state graphs (the harvested ys930-sized states, tiled), this rank's shard scored in one fused
+    launch, then the all_gather.  Returns candidates/s over all ranks (max over ranks, device-timed)."""
+    from meshdqn_b200.data import Batch
+    from meshdqn_b200.parallel import max_over_ranks, shard_range
+    import torch.distributed as dist
+    st = rb_dev.states
+    nb = int(st.ptr.numel()) - 1
+    lo, hi = shard_range(total, rank, world)
+    nloc = hi - lo
+    reps = (nloc + nb - 1) // nb
+    N, E = int(st.x.shape[0]), int(st.edge_index.shape[1])
+    x = st.x.repeat(reps, 1)
+    rr = torch.arange(reps, device=dev)
+    ei = (st.edge_index.unsqueeze(0) + (rr * N).view(-1, 1, 1)).permute(1, 0, 2).reshape(2, -1).contiguous()
+    p0, e0 = st.ptr.to(dev).long(), st.eptr.to(dev).long()
+    ptr = torch.cat([(p0[:-1].unsqueeze(0) + (rr * N).view(-1, 1)).reshape(-1), torch.tensor([reps * N], device=dev)])
+    eptr = torch.cat([(e0[:-1].unsqueeze(0) + (rr * E).view(-1, 1)).reshape(-1), torch.tensor([reps * E], device=dev)])
+    b = Batch(x=x, edge_index=ei)
+    b.batch = torch.repeat_interleave(torch.arange(reps * nb, device=dev), ptr[1:] - ptr[:-1])
+    b.ptr, b.eptr, b.num_graphs = ptr, eptr, reps * nb
+    table = torch.empty((world, reps * nb, 2), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def run():
+        am, q = net.select_action(b)
+        loc = torch.stack([am.float(), q.max(1).values], 1)
+        if world > 1:
+            dist.all_gather_into_tensor(table.view(-1, 2), loc)
+        return loc
+    with torch.no_grad():
+        for _ in range(3):
+            run()
+        ms = time_events(run, 10, flush)
+    ms = max_over_ranks(ms, dev)
+    n_eval = reps * nb * world
+    return {"candidates": n_eval, "per_gpu": reps * nb, "ms": ms, "candidates_per_s": n_eval / (ms * 1e-3),
+            "nodes_per_graph": 180, "collective": "one all_gather of (action, q) per candidate" if world > 1 else "none (1 GPU)"}
+
+
 def measure_extras(dev, net, rb_dev, flush, args):
     """Secondary numbers of BASELINE.json's metric: Q-eval graphs/s, ys930 env steps/s, re-interp vertices/s."""
     from meshdqn_b200.Env2DAirfoil import SourceField
@@ -397,6 +436,72 @@ def measure_extras(dev, net, rb_dev, flush, args):
     T = 5
     alg = 16 * m2.nv + 8 * m2.ne + 16 * m0.nv + 36 * m0.nc + 8 * T * (2 * (m0.nv + m0.ne) + m0.nv) + \
         8 * T * (2 * npt + m2.nv) + 4 * npt
+    # ---- BASELINE.json configs[3]: Q-evaluation of ONE large state graph (all vertices of the synthetic mesh) through the
+    # layered path: CSR message passing + tcgen05 3xTF32 node GEMMs + radix-select TopK (gnn_layered.cu)
+    from meshdqn_b200 import _lib
+    from meshdqn_b200.data import Data
+    from meshdqn_b200.synthetic import field_values
+    u, pr = field_values(coords, 5, 0)
+    xg = np.concatenate([coords, u.transpose(1, 0, 2).reshape(len(coords), -1), pr.T], axis=1).astype(np.float32)
+    cc = cells.astype(np.int64)
+    eig = np.stack([np.stack([cc[:, 0], cc[:, 0], cc[:, 1]], 1).ravel(), np.stack([cc[:, 1], cc[:, 2], cc[:, 2]], 1).ravel()])
+    big = Data(x=torch.from_numpy(xg), edge_index=torch.from_numpy(eig)).to(dev)
+    Ng, Eg = int(big.x.shape[0]), int(big.edge_index.shape[1])
+    lay = {"nodes": Ng, "directed_edges": Eg, "features": 17}
+    with torch.no_grad():
+        for gemm in ("tf32x3", "fp32"):
+            net.layered_gemm = gemm
+            for _ in range(3):
+                net.select_action(big)
+            gq = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gq):
+                net.select_action(big)
+            msq = time_events(gq.replay, 10, flush)
+            lay[f"q_eval_ms_{gemm}"] = msq
+            lay[f"nodes_per_s_{gemm}"] = Ng / (msq * 1e-3)
+        net.layered_gemm = "tf32x3"
+    # message-passing kernel alone (SAGEConv aggregation over the CSR), against the HBM roofline
+    L, p = _lib.lib(), _lib.ptr
+    src32 = big.edge_index[0].to(torch.int32).contiguous()
+    dst32 = big.edge_index[1].to(torch.int32).contiguous()
+    ecount = torch.tensor([Eg], dtype=torch.int32, device=dev)
+    row_ptr = torch.empty(Ng + 1, dtype=torch.int32, device=dev)
+    colx = torch.empty(Eg, dtype=torch.int32, device=dev)
+    scr = torch.empty(int(L.mdq_csr_build_scratch_words(Eg, Ng)), dtype=torch.int32, device=dev)
+    _lib.check(L.mdq_csr_build(p(src32), p(dst32), p(ecount), Eg, Ng, p(row_ptr), p(colx), p(scr), _lib.stream_ptr()))
+    Amat = torch.empty(Ng, 40, device=dev)
+    fa = lambda: _lib.check(L.mdq_sage_aggregate(p(big.x), 17, 0, 17, p(row_ptr), p(colx), Ng, p(Amat), 40, _lib.stream_ptr()))
+    fa()
+    msa = time_events(fa, 10, flush)
+    alg_mp = 4 * (2 * Ng * 17 + Eg + Ng + 1)          # features read once, aggregate written once, CSR indices
+    lay["message_passing_17"] = {"us": msa * 1e3, "algorithmic_bytes": alg_mp, "achieved_GBps": alg_mp / (msa * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": alg_mp / (msa * 1e-3) / 1e9 / hbm}
+    n1 = Ng // 10                                       # the pooled level's shape: 128-wide rows, N/10 nodes
+    keep = (big.edge_index[0] < n1) & (big.edge_index[1] < n1)
+    s1, d1 = src32[keep].contiguous(), dst32[keep].contiguous()
+    e1 = int(s1.numel())
+    ec1 = torch.tensor([e1], dtype=torch.int32, device=dev)
+    rp1 = torch.empty(n1 + 1, dtype=torch.int32, device=dev)
+    cl1 = torch.empty(max(e1, 1), dtype=torch.int32, device=dev)
+    sc1 = torch.empty(int(L.mdq_csr_build_scratch_words(e1, n1)), dtype=torch.int32, device=dev)
+    _lib.check(L.mdq_csr_build(p(s1), p(d1), p(ec1), e1, n1, p(rp1), p(cl1), p(sc1), _lib.stream_ptr()))
+    x1 = torch.randn(n1, 128, device=dev)
+    A1 = torch.empty(n1, 256, device=dev)
+    fb = lambda: _lib.check(L.mdq_sage_aggregate(p(x1), 128, 0, 128, p(rp1), p(cl1), n1, p(A1), 256, _lib.stream_ptr()))
+    fb()
+    msb = time_events(fb, 10, flush)
+    alg_mp1 = 4 * (2 * n1 * 128 + e1 + n1 + 1)
+    lay["message_passing_128"] = {"us": msb * 1e3, "rows": n1, "algorithmic_bytes": alg_mp1,
+                                  "achieved_GBps": alg_mp1 / (msb * 1e-3) / 1e9, "frac_of_hbm_peak": alg_mp1 / (msb * 1e-3) / 1e9 / hbm}
+    out["q_eval_large_graph"] = lay
+    del big, Amat, A1, x1
+    # ---- BASELINE.json configs[4]: batched candidate evaluation, 8192 candidate state graphs sharded by graph over
+    # the ranks (1024 per GPU at 8 GPUs), fused Q-kernel + one all_gather of (action, q) per candidate
+    from meshdqn_b200.parallel import evaluate_candidates
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    out["candidate_batch"] = bench_candidates(net, rb_dev, dev, rank, world, flush)
     out["reinterp_synthetic"] = {"triangles": int(m0.nc), "target_points": npt, "vertices_per_s": npt / (ms * 1e-3),
                                  "ms_per_launch": ms, "algorithmic_bytes": alg, "achieved_GBps": alg / (ms * 1e-3) / 1e9,
                                  "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / hbm,

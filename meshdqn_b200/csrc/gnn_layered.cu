@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned *__
     __syncwarp();
     const int wbase = blockIdx.x * RS_TILE + warp * PER_WARP;
     for (int q = 0; q < PER_WARP; q += 32) {
+        if (wbase + q >= n) break;                       // warp-uniform: nothing left in this chunk
         const int i = wbase + q + lane;
         const int d = (i < n) ? (int)((key[i] >> shift) & 255) : 256 + lane;
         const unsigned peers = __match_any_sync(FULL, d);
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned *__
     }
     __syncthreads();
     for (int q = 0; q < PER_WARP; q += 32) {
+        if (wbase + q >= n) break;
         const int i = wbase + q + lane;
         unsigned k = 0;
         int d = 256 + lane;
@@ -552,18 +554,28 @@ __global__ void __launch_bounds__(256) k_select_hist(const unsigned *__restrict_
 }
 __global__ void __launch_bounds__(256) k_select_pick(SelState *st, int *__restrict__ hist, int shift)
 {
-    __shared__ int h[256];
-    h[threadIdx.x] = hist[threadIdx.x];
-    __syncthreads();
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = hist[threadIdx.x];
     hist[threadIdx.x] = 0;   // ready for the next pass
-    if (threadIdx.x == 0) {
-        int cum = 0, d = 0;
-        const int need = st->remaining;
-        for (; d < 255; ++d) {
-            if (cum + h[d] >= need) break;
-            cum += h[d];
-        }
-        st->prefix |= (unsigned)d << shift;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    incl += off;
+    const int need = st->remaining;
+    __syncthreads();
+    // the digit whose cumulative count first reaches `need` (the last digit if rounding left it short)
+    const bool hit = (incl >= need && incl - c < need) || (threadIdx.x == 255 && incl < need);
+    if (hit) {
+        const int cum = incl - c;
+        st->prefix |= (unsigned)threadIdx.x << shift;
         st->mask |= 255u << shift;
         st->remaining = need - cum;
         st->count_lt += cum;

@@ -168,8 +168,10 @@ def test_layered_matches_fused_on_a_graph_both_can_run(cuda_device):
         for gemm in ("fp32", "tf32x3"):
             net.layered_gemm = gemm
             q_lay, _, am = net._launch_forward_layered(x, ei, False, True)
-            rel = float(((q_lay.cpu() - q_fused).abs() / q_fused.abs().clamp_min(1e-30)).max())
+            ok = q_fused > 1e-30
+            rel = float(((q_lay.cpu() - q_fused).abs() / q_fused)[ok].max())
             assert rel < (5e-5 if gemm == "fp32" else 5e-4), (gemm, rel)   # two fp32 summation orders / 3xTF32
             assert int(am[0]) == int(q_fused.argmax())
         q_ref = ref(d.to("cpu"))
-    assert float(((q_fused - q_ref).abs() / q_ref.abs().clamp_min(1e-30)).max()) < 1e-5
+    big = q_ref > 1e-30                      # entries the fp32 softmax can represent without underflow
+    assert float(((q_fused - q_ref).abs() / q_ref)[big].max()) < 1e-5
