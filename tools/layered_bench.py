@@ -30,7 +30,12 @@ def timed(fn, iters, flush_buf):
     ts = []
     for _ in range(iters):
         if flush_buf is not None:
-            flush_buf.fill_(1)
+            mode = os.environ.get("FLUSH", "write")
+            if mode == "write":
+                flush_buf.fill_(1)          # leaves L2 full of DIRTY lines: the timed kernel also pays their write-back
+            elif mode == "read":
+                flush_buf.view(torch.int64).sum()   # L2 full of clean lines
+
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
