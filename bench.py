@@ -245,13 +245,34 @@ def run_ours(args):
     ms_step = ms_total / K
     value = world * BATCH / (ms_step * 1e-3)
 
-    # ---- e2e: pinned host batch -> device, step, loss read-back, every step ----
-    for _ in range(2):
-        float(trainer.step(rb_host.to(dev)))
+    # ---- e2e: every step copies its (pinned) host batch to the device and reads the step's loss back.  The copy of
+    # step k+1 runs on a side stream while step k computes (DevicePrefetcher), and the loss of step k is read (pinned
+    # D2H + event) while step k+1 is already enqueued -- the public training-loop API a user would call ----
+    from meshdqn_b200.replay import DevicePrefetcher
+    pf = DevicePrefetcher(dev)
+    loss_host = torch.zeros(K + 4, dtype=torch.float32).pin_memory()
+
+    def e2e_loop(n):
+        pf.submit(rb_host)
+        evs = []
+        for k in range(n):
+            rb = pf.take()
+            if k + 1 < n:
+                pf.submit(rb_host)
+            loss = trainer.step(rb)
+            loss_host[k:k + 1].copy_(loss, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            evs.append(ev)
+            if k >= 1:
+                evs[k - 1].synchronize()      # the previous step's loss is on the host now
+                float(loss_host[k - 1])
+        evs[-1].synchronize()
+        return float(loss_host[n - 1])
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        float(trainer.step(rb_host.to(dev)))
+    e2e_loop(K)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     e2e_val = world * BATCH * K / e2e_s

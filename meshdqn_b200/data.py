@@ -74,6 +74,34 @@ class Batch(Data):
         out.num_graphs = len(data_list)
         return out
 
+    def _host_meta(self):
+        """(ptr i32, eptr i32, B, max_n, max_e) from the HOST offset vectors -- what the kernels need to address one
+        graph per CTA; computed once per collated batch so that moving it to a device never synchronises."""
+        m = self.__dict__.get("_meta")
+        if m is None and getattr(self, "ptr", None) is not None and not self.ptr.is_cuda:
+            ptr, eptr = self.ptr, self.eptr
+            m = (ptr.to(torch.int32), eptr.to(torch.int32), int(ptr.numel()) - 1,
+                 int((ptr[1:] - ptr[:-1]).max()) if ptr.numel() > 1 else 0,
+                 int((eptr[1:] - eptr[:-1]).max()) if eptr.numel() > 1 else 0)
+            self.__dict__["_meta"] = m
+        return m
+
+    def pin_memory(self):
+        m = self._host_meta()
+        out = super().pin_memory()
+        if m is not None:
+            out.__dict__["_meta"] = (m[0].pin_memory(), m[1].pin_memory()) + m[2:]
+        return out
+
+    def to(self, device, non_blocking=False):
+        m = self._host_meta()
+        out = super().to(device, non_blocking=non_blocking)
+        out.__dict__.pop("_mdq_ptrs", None)
+        if m is not None and torch.device(device).type == "cuda":
+            out.__dict__["_mdq_ptrs"] = (m[0].to(device, non_blocking=non_blocking), m[1].to(device, non_blocking=non_blocking),
+                                         m[2], m[3], m[4])
+        return out
+
 
 class DataLoader:
     """``DataLoader(list_of_Data, batch_size)`` -> iterates ``Batch`` objects (no shuffling by

@@ -74,6 +74,15 @@ class ReplayBatch:
                            self.next_slot.to(device, non_blocking=non_blocking),
                            self.rewards.to(device, non_blocking=non_blocking), self.owner.to(device, non_blocking=non_blocking))
 
+    def tensors(self):
+        out = [self.actions, self.next_slot, self.rewards, self.owner]
+        for b in (self.states, self.next_states):
+            if b is None:
+                continue
+            out += [v for v in b.__dict__.values() if torch.is_tensor(v)]
+            out += [v for v in (b.__dict__.get("_mdq_ptrs") or ()) if torch.is_tensor(v)]
+        return out
+
     def h2d_bytes(self):
         n = 0
         for b in (self.states, self.next_states):
@@ -82,6 +91,34 @@ class ReplayBatch:
             n += b.x.numel() * b.x.element_size() + b.edge_index.numel() * 8 + b.ptr.numel() * 8 + b.eptr.numel() * 8 + \
                 b.batch.numel() * 8
         return n + self.actions.numel() * 4 + self.next_slot.numel() * 4 + self.rewards.numel() * 4 + self.owner.numel() * 4
+
+
+class DevicePrefetcher:
+    """Host -> device staging of replay minibatches on a side stream, one batch ahead of the training step
+    (the collated ``ReplayBatch`` must be pinned).  ``submit(host_batch)`` starts the copies, ``take()`` makes the
+    current stream wait for them and hands the device batch over; with a ~10 MB batch the PCIe copy of step k+1
+    overlaps the kernels of step k instead of preceding them."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._pending = None
+
+    def submit(self, host_batch: "ReplayBatch"):
+        with torch.cuda.stream(self.stream):
+            dev = host_batch.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (dev, ev)
+
+    def take(self) -> "ReplayBatch":
+        dev, ev = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev.tensors():          # allocated on the side stream, consumed on the current one
+            t.record_stream(cur)
+        return dev
 
 
 def multistep_lr(base_lr, step, milestones=(500000, 1000000, 1500000), gamma=0.1):

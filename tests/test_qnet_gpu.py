@@ -157,6 +157,12 @@ def test_backward_matches_autograd_oracle(cuda_device):
 def test_too_large_graph_fails_loudly(cuda_device):
     net, _ = make_nets(cuda_device)
     g = torch.Generator().manual_seed(1)
-    d = rand_graph(g, n=4000, e=8000)
+    from meshdqn_b200.data import Batch
+    # a BATCH containing a graph that does not fit one CTA's shared memory: no silent fallback, a loud error
+    # (a SINGLE large graph takes the layered path instead, tests/test_layered_gpu.py)
+    b = Batch.from_data_list([rand_graph(g, n=4000, e=8000), rand_graph(g, n=100, e=200)])
     with pytest.raises(RuntimeError, match="shared memory"):
-        net(d.to(cuda_device))
+        with torch.no_grad():
+            net(b.to(cuda_device))
+    with pytest.raises(NotImplementedError):          # the layered path is forward-only
+        net(rand_graph(g, n=4000, e=8000).to(cuda_device))
