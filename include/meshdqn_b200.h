@@ -229,7 +229,7 @@ int mdq_interpolate(const double *coords, int nv, const int32_t *edges, int ne, 
  * so one CTA stages a leaf in shared memory with bulk (TMA) copies and serves every target point inside it. */
 typedef struct {
     int32_t n_leaves, depth, T;
-    int32_t max_nv, max_np2, max_nc, max_nbin, max_nent; /* padded per-leaf maxima (shared-memory sizing) */
+    int32_t max_nv, max_np2, max_nc, max_nbin, max_nent; /* padded per-leaf maxima (informational) */
     int64_t u_stride, p_stride;                          /* rows of UL / PL per snapshot */
     const double *tree;         /* [n_leaves-1] split planes, heap order, split axis in the mantissa LSB */
     const int32_t *leaf_info;   /* [n_leaves][16] */
@@ -243,6 +243,10 @@ typedef struct {
     const uint16_t *binsL;      /* micro-grid candidate lists (local cell ids, ascending) */
     const int32_t *leaf_base;   /* [n_leaves+1] target-record bucket offsets (capacity prefix sums) */
     int64_t total_cap;          /* = leaf_base[n_leaves] */
+    int32_t smem_bytes;         /* dynamic shared memory per CTA: sized for the typical leaf so that several CTAs share an
+                                 * SM; a leaf whose own sections need more is served from HBM by the same CTA
+                                 * (0: size for the largest leaf, from the maxima above) */
+    int32_t reserved;
 } mdq_tile_index_t;
 
 /* Workspace of mdq_interpolate_tiled, in int32 words:

@@ -112,16 +112,15 @@ class SourceField:
             ti = build_tile_index(m.coordinates(), m.cells_host(), m.cell_edges.cpu().numpy(), m.ne,
                                   np.asarray(U0, dtype=np.float64), np.asarray(P0, dtype=np.float64), k,
                                   bins_per_cell=self.micro_bins_per_cell, bucket_factor=self.bucket_factor)
-            probe = _lib.mdq_tile_index_t()
-            probe.T = ti.T
-            probe.max_nv, probe.max_np2, probe.max_nc = ti.max_nv, ti.max_np2, ti.max_nc
-            probe.max_nbin, probe.max_nent = ti.max_nbin, ti.max_nent
-            smem = int(L.mdq_interp_tiled_smem_bytes(ctypes.byref(probe)))
-            # the largest leaf sizes every CTA's shared memory: keep two CTAs resident per SM (<= 113 KB each);
-            # an explicit leaf_cells request is honoured as long as one CTA fits at all
-            if smem <= 113 * 1024 or k <= 32 or not self.auto_leaf:
+            # the per-CTA shared memory is sized for the typical leaf (tile_index.pick_smem); an index whose leaves
+            # mostly exceed one CTA's 227 KB is rebuilt with smaller leaves (an explicit leaf_cells request raises)
+            if ti.smem_bytes > 0 or k <= 32:
                 break
+            if not self.auto_leaf:
+                raise RuntimeError(f"leaf_cells={k}: fewer than 98% of the leaves fit 227 KB of shared memory")
             k //= 2
+        if ti.smem_bytes <= 0:
+            raise RuntimeError("tile index: leaves do not fit shared memory even at 32 cells per leaf")
         self.leaf_cells = k
         self.tile_host = ti
         dev = {k: torch.from_numpy(np.ascontiguousarray(getattr(ti, k))).to(d)
@@ -134,6 +133,7 @@ class SourceField:
         c.n_leaves, c.depth, c.T = ti.n_leaves, ti.depth, ti.T
         c.max_nv, c.max_np2, c.max_nc, c.max_nbin, c.max_nent = ti.max_nv, ti.max_np2, ti.max_nc, ti.max_nbin, ti.max_nent
         c.u_stride, c.p_stride, c.total_cap = ti.u_stride, ti.p_stride, ti.total_cap
+        c.smem_bytes = ti.smem_bytes
         for k, t in dev.items():
             setattr(c, k, t.data_ptr())
         self.tile = c

@@ -50,7 +50,8 @@ class mdq_tile_index_t(Structure):
                 ("max_nc", c_int32), ("max_nbin", c_int32), ("max_nent", c_int32), ("u_stride", c_int64),
                 ("p_stride", c_int64), ("tree", c_void_p), ("leaf_info", c_void_p), ("leaf_rect", c_void_p),
                 ("coordsL", c_void_p), ("UL", c_void_p), ("PL", c_void_p), ("gidL", c_void_p), ("cvL", c_void_p),
-                ("binptrL", c_void_p), ("binsL", c_void_p), ("leaf_base", c_void_p), ("total_cap", c_int64)]
+                ("binptrL", c_void_p), ("binsL", c_void_p), ("leaf_base", c_void_p), ("total_cap", c_int64),
+                ("smem_bytes", c_int32), ("reserved", c_int32)]
 
 
 def _newer(src, dst):

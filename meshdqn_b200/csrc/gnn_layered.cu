@@ -17,6 +17,7 @@
 // One graph per call (B = 1); every size the launches need is known on the host (n_{l+1} = ceil(ratio * n_l) in
 // float32, as PyG computes it), edge counts stay on the device.  No host synchronisation inside.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -263,6 +264,74 @@ __global__ void __launch_bounds__(256) k_sage_rows_vec4(const int *__restrict__ 
         // columns beyond 2 Fp (lda rounded up for the tensor-core K step) are zeroed by the chunk-0 thread
         if (c == 0)
             for (int k = 8 * ch; k < lda; ++k) A[(size_t)r * lda + k] = 0.f;
+    }
+}
+
+// Narrow rows in ONE pass (the default): a CTA owns RB consecutive output rows and builds their [x | mean | 0-pad]
+// GEMM-operand rows in shared memory, then writes the tile as one contiguous block of float4 (rows are consecutive,
+// so RB*lda floats are contiguous in A: every store is a full, coalesced 512-byte warp request; no partial sectors,
+// no second pass over A).  The tile's CSR slice (row_ptr and the col entries of its rows, contiguous in memory) is
+// staged in shared memory first, so the gather phase has a single level of global-memory latency: thread per
+// (row, feature), consecutive lanes read consecutive floats of a neighbour's unpadded 4F-byte row, eight neighbour
+// loads in flight per thread, summed sequentially in CSR (= edge) order as torch_scatter's CPU loop does.
+constexpr int ST_RB = 128;      // rows per tile
+constexpr int ST_ECAP = 2048;   // staged col entries per tile (mean degree <= 16); larger tiles read col from global memory
+template <int CH>
+__global__ void __launch_bounds__(256) k_sage_rows_tile(const float *__restrict__ X, int ldx, int col0, int F,
+                                                        const int *__restrict__ row_ptr, const int *__restrict__ col,
+                                                        int n_rows, int ch_rt, float *__restrict__ A, int lda)
+{
+    extern __shared__ float4 st_smem4[];
+    float *tile = reinterpret_cast<float *>(st_smem4);              // [ST_RB][lda]
+    int *s_rp = reinterpret_cast<int *>(tile + ST_RB * lda);        // [ST_RB + 1]
+    int *s_col = s_rp + ST_RB + 4;                                  // [ST_ECAP]
+    const int Fp = 4 * (CH > 0 ? CH : ch_rt);
+    const int tid = threadIdx.x;
+    for (int r0 = blockIdx.x * ST_RB; r0 < n_rows; r0 += gridDim.x * ST_RB) {
+        const int nr = min(ST_RB, n_rows - r0);
+        for (int i = tid; i <= nr; i += 256) s_rp[i] = __ldg(row_ptr + r0 + i);
+        __syncthreads();
+        const int e0 = s_rp[0], ne = s_rp[nr] - e0;
+        const bool staged = ne <= ST_ECAP;
+        if (staged)
+            for (int i = tid; i < ne; i += 256) s_col[i] = __ldg(col + e0 + i);
+        for (int i = tid; i < nr * (lda - 2 * Fp); i += 256) {       // columns beyond 2 Fp (lda rounded up for the K step)
+            const int r = i / (lda - 2 * Fp);
+            tile[r * lda + 2 * Fp + (i - r * (lda - 2 * Fp))] = 0.f;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * Fp; idx += 256) {
+            const int r = idx / Fp, f = idx - r * Fp;
+            float xs = 0.f, m = 0.f;
+            if (f < F) {
+                const float *Xf = X + col0 + f;
+                xs = __ldg(Xf + (size_t)(r0 + r) * ldx);
+                const int a = s_rp[r] - e0, b = s_rp[r + 1] - e0;
+                float s = 0.f;
+                for (int e = a; e < b; e += 8) {
+                    int j[8];
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {     // clamped (always valid) indices; the surplus loads are not added
+                        const int ee = min(e + q, b - 1);
+                        j[q] = staged ? s_col[ee] : __ldg(col + e0 + ee);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = __ldg(Xf + (size_t)j[q] * ldx);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (e + q < b) s += v[q];
+                }
+                m = s / (float)max(b - a, 1);
+            }
+            tile[r * lda + f] = xs;
+            tile[r * lda + Fp + f] = m;
+        }
+        __syncthreads();
+        float4 *dst = reinterpret_cast<float4 *>(A + (size_t)r0 * lda);
+        const int n4 = nr * (lda >> 2);
+        for (int i = tid; i < n4; i += 256) dst[i] = st_smem4[i];
+        __syncthreads();
     }
 }
 
@@ -929,6 +998,14 @@ int sage_rows(const float *X, int ldx, int col0, int F, const int *row_ptr, cons
             return MDQ_EINVAL;
         }
         int rc;
+        static const bool two_pass = getenv("MDQ_SAGE_TWOPASS") != nullptr;   // the older pad + gather pair, kept for A/B timing
+        const size_t tile_bytes = sizeof(float) * (size_t)ST_RB * lda + sizeof(int) * (ST_RB + 4 + ST_ECAP);
+        if (!two_pass && tile_bytes <= 48 * 1024) {
+            const int gridt = grid_for(n, ST_RB, 148 * 8);
+            if (ch == 5) k_sage_rows_tile<5><<<gridt, 256, tile_bytes, st>>>(X, ldx, col0, F, row_ptr, col, n, ch, A, lda);
+            else k_sage_rows_tile<0><<<gridt, 256, tile_bytes, st>>>(X, ldx, col0, F, row_ptr, col, n, ch, A, lda);
+            return mdq::check_launch("k_sage_rows_tile");
+        }
         const int grid = grid_for((long long)n * ch, 256, 148 * 64);
         if (ch == 5) k_pad_rows<5><<<grid, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);
         else k_pad_rows<0><<<grid, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);

@@ -33,7 +33,7 @@ struct TileArgs {
     const int *leaf_base;       // [n_leaves+1] bucket offsets (capacity prefix sums)
     long long u_stride, p_stride;
     int n_leaves, depth;
-    int max_nv, max_np2, max_nc, max_nbin, max_nent;
+    int smem_cap;               // dynamic shared memory of this launch; a leaf that needs more is served from HBM
     int *leaf_cnt;              // [n_leaves] zero on entry, zero again on exit
     int *ovf_count;             // zero on entry / exit
     unsigned int *ticket;       // zero on entry / exit
@@ -180,34 +180,62 @@ __device__ __forceinline__ void tile_locate_eval(const InterpArgs &a, const Leaf
     }
 }
 
+// Four points per thread, interleaved: the k-d descent is a chain of `depth` dependent (L1-resident) loads and the slot
+// allocation a chain of match -> atomic -> two bucket-offset loads, so one point per thread leaves the SM waiting on
+// latency; four independent chains per thread keep four times as many loads and atomics in flight.
+constexpr int CLS_PPT = 4;
 __global__ void __launch_bounds__(256) k_tile_classify(const TileArgs t)
 {
     const int np = t.a.nv + t.a.ne;
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) *t.a.miss_count = 0;
-    for (int i0 = blockIdx.x * blockDim.x; i0 < np; i0 += gridDim.x * blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        int leaf = -1 - lane;  // distinct dummy keys for the tail lanes
-        double px = 0.0, py = 0.0;
-        if (i < np) {
-            target_point(t.a, i, px, py);
-            leaf = tile_leaf_of(t.tree, t.depth, px, py);
+    for (int i0 = blockIdx.x * (256 * CLS_PPT); i0 < np; i0 += gridDim.x * (256 * CLS_PPT)) {
+        int idx[CLS_PPT], node[CLS_PPT];
+        double px[CLS_PPT], py[CLS_PPT];
+#pragma unroll
+        for (int q = 0; q < CLS_PPT; ++q) {
+            idx[q] = i0 + q * 256 + (int)threadIdx.x;
+            px[q] = py[q] = 0.0;
+            node[q] = 0;
+            if (idx[q] < np) target_point(t.a, idx[q], px[q], py[q]);
+        }
+        for (int l = 0; l < t.depth; ++l) {
+#pragma unroll
+            for (int q = 0; q < CLS_PPT; ++q) {
+                const double s = __ldg(t.tree + node[q]);
+                const int d = (int)(__double_as_longlong(s) & 1LL);
+                const double v = d ? py[q] : px[q];
+                node[q] = 2 * node[q] + 1 + (v >= s ? 1 : 0);
+            }
         }
         // warp-aggregated slot allocation: one atomic per distinct leaf in the warp (spatially ordered targets
-        // put most of a warp in one leaf)
-        const unsigned peers = __match_any_sync(FULL, leaf);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader && leaf >= 0) base = atomicAdd(t.leaf_cnt + leaf, __popc(peers));
-        base = __shfl_sync(FULL, base, leader);
-        if (i < np) {
-            const int slot = base + __popc(peers & ((1u << lane) - 1u));
-            const int b0 = __ldg(t.leaf_base + leaf), b1 = __ldg(t.leaf_base + leaf + 1);
-            if (slot < b1 - b0) {
-                t.rec_xy[b0 + slot] = make_double2(px, py);
-                t.rec_id[b0 + slot] = i;
-            } else {
-                t.ovf_list[atomicAdd(t.ovf_count, 1)] = i;
+        // put most of a warp in one leaf); tail lanes carry distinct dummy keys and allocate nothing
+        int leaf[CLS_PPT], base[CLS_PPT], rank[CLS_PPT], leader[CLS_PPT], b0[CLS_PPT], b1[CLS_PPT];
+#pragma unroll
+        for (int q = 0; q < CLS_PPT; ++q) {
+            leaf[q] = idx[q] < np ? node[q] - ((1 << t.depth) - 1) : -1 - lane;
+            const unsigned peers = __match_any_sync(FULL, leaf[q]);
+            leader[q] = __ffs(peers) - 1;
+            rank[q] = __popc(peers & ((1u << lane) - 1u));
+            base[q] = 0;
+            b0[q] = b1[q] = 0;
+            if (leaf[q] >= 0) {
+                if (lane == leader[q]) base[q] = atomicAdd(t.leaf_cnt + leaf[q], __popc(peers));
+                b0[q] = __ldg(t.leaf_base + leaf[q]);
+                b1[q] = __ldg(t.leaf_base + leaf[q] + 1);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CLS_PPT; ++q) {
+            const int bs = __shfl_sync(FULL, base[q], leader[q]);
+            if (idx[q] < np) {
+                const int slot = bs + rank[q];
+                if (slot < b1[q] - b0[q]) {
+                    t.rec_xy[b0[q] + slot] = make_double2(px[q], py[q]);
+                    t.rec_id[b0[q] + slot] = idx[q];
+                } else {
+                    t.ovf_list[atomicAdd(t.ovf_count, 1)] = idx[q];
+                }
             }
         }
     }
@@ -215,26 +243,14 @@ __global__ void __launch_bounds__(256) k_tile_classify(const TileArgs t)
 
 constexpr int TILE_THREADS = 512;
 
-// shared-memory carve-up (bytes), identical on host and device
-struct TileSmem {
-    int off_coords, off_U, off_P, off_gid, off_cv, off_binptr, off_bins, total;
-};
-__host__ __device__ inline TileSmem tile_smem(int max_nv, int max_np2, int max_nc, int max_nbin, int max_nent, int T)
+// Bytes of shared memory leaf L needs: mbarrier + its own (padded) sections, carved up in the order below.
+__host__ __device__ inline unsigned tile_leaf_bytes(int nv, int np2, int nc, int nbin, int nent, int T)
 {
-    TileSmem s;
-    int o = 16;  // mbarrier
-    s.off_coords = o; o += 16 * max_nv;
-    s.off_U = o;      o += 16 * max_np2 * T;
-    s.off_P = o;      o += 8 * max_nv * T;      // max_nv is even -> 16-byte multiples
-    s.off_gid = o;    o += 4 * max_nc;          // max_nc multiple of 4
-    s.off_cv = o;     o += 12 * max_nc;
-    s.off_binptr = o; o += 2 * max_nbin;        // multiples of 8 entries
-    s.off_bins = o;   o += 2 * max_nent;
-    s.total = o;
-    return s;
+    return 16u + 16u * nv + (unsigned)T * (16u * np2 + 8u * nv) + 16u * nc + 2u * nbin + 2u * nent;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_interp(const TileArgs t)
+template <int NT, int MINB>   // CTA size / CTAs per SM the register budget is set for
+__global__ void __launch_bounds__(NT, MINB) k_tile_interp(const TileArgs t)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int L = blockIdx.x;
@@ -251,35 +267,43 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_interp(const TileArgs 
     if (cnt == 0) return;
     const InterpArgs &a = t.a;
     const int T = a.T;
-    const TileSmem S = tile_smem(t.max_nv, t.max_np2, t.max_nc, t.max_nbin, t.max_nent, T);
+    const int vbase = i0.x, nvl = i0.y, dbase = i0.z, np2l = i0.w, cbase = i1.x, ncl = i1.y, bbase = i1.z, nbin = i1.w;
+    const int ebase = i2.x, nent = i2.y;
+    // The carve-up follows the leaf's OWN section sizes (every section is a 16-byte multiple), so the launch is sized
+    // for the typical leaf (four CTAs per SM) and not for the largest one; the rare leaf that does not fit
+    // (large cells overlapping many leaves) is served by this CTA straight from the leaf arrays in HBM.
+    const bool staged = tile_leaf_bytes(nvl, np2l, ncl, nbin, nent, T) <= (unsigned)t.smem_cap;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
-    double2 *s_xy = reinterpret_cast<double2 *>(smem + S.off_coords);
-    double2 *s_U = reinterpret_cast<double2 *>(smem + S.off_U);
-    double *s_P = reinterpret_cast<double *>(smem + S.off_P);
-    int *s_gid = reinterpret_cast<int *>(smem + S.off_gid);
-    unsigned *s_cv = reinterpret_cast<unsigned *>(smem + S.off_cv);
-    unsigned short *s_bp = reinterpret_cast<unsigned short *>(smem + S.off_binptr);
-    unsigned short *s_bins = reinterpret_cast<unsigned short *>(smem + S.off_bins);
-    const int nvl = i0.y, np2l = i0.w;
-    if (threadIdx.x == 0) {
-        const int vbase = i0.x, dbase = i0.z, cbase = i1.x, ncl = i1.y, bbase = i1.z, nbin = i1.w;
-        const int ebase = i2.x, nent = i2.y;
-        mbar_init(bar, 1);
-        const unsigned bytes = 16u * nvl + (unsigned)T * (16u * np2l + 8u * nvl) + 16u * ncl + 2u * nbin + 2u * nent;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(s_bp, t.binptrL + bbase, 2u * nbin, bar);
-        bulk_g2s(s_bins, t.binsL + ebase, 2u * nent, bar);
-        bulk_g2s(s_cv, t.cvL + 6 * (size_t)cbase, 12u * ncl, bar);
-        bulk_g2s(s_xy, t.coordsL + vbase, 16u * nvl, bar);
-        bulk_g2s(s_gid, t.gidL + cbase, 4u * ncl, bar);
-        for (int k = 0; k < T; ++k) {
-            bulk_g2s(s_U + (size_t)k * np2l, t.UL + (size_t)k * t.u_stride + dbase, 16u * np2l, bar);
-            bulk_g2s(s_P + (size_t)k * nvl, t.PL + (size_t)k * t.p_stride + vbase, 8u * nvl, bar);
-        }
-    }
     LeafView v;
-    v.xy = s_xy; v.U = s_U; v.P = s_P; v.gid = s_gid; v.cv = s_cv; v.bp = s_bp; v.bins = s_bins;
-    v.u_rows = np2l; v.p_rows = nvl;
+    if (staged) {
+        double2 *s_xy = reinterpret_cast<double2 *>(smem + 16);
+        double2 *s_U = s_xy + nvl;
+        double *s_P = reinterpret_cast<double *>(s_U + (size_t)np2l * T);
+        int *s_gid = reinterpret_cast<int *>(s_P + (size_t)nvl * T);
+        unsigned *s_cv = reinterpret_cast<unsigned *>(s_gid + ncl);
+        unsigned short *s_bp = reinterpret_cast<unsigned short *>(s_cv + 3 * ncl);
+        unsigned short *s_bins = s_bp + nbin;
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, tile_leaf_bytes(nvl, np2l, ncl, nbin, nent, T) - 16u);
+            bulk_g2s(s_bp, t.binptrL + bbase, 2u * nbin, bar);
+            bulk_g2s(s_bins, t.binsL + ebase, 2u * nent, bar);
+            bulk_g2s(s_cv, t.cvL + 6 * (size_t)cbase, 12u * ncl, bar);
+            bulk_g2s(s_xy, t.coordsL + vbase, 16u * nvl, bar);
+            bulk_g2s(s_gid, t.gidL + cbase, 4u * ncl, bar);
+            for (int k = 0; k < T; ++k) {
+                bulk_g2s(s_U + (size_t)k * np2l, t.UL + (size_t)k * t.u_stride + dbase, 16u * np2l, bar);
+                bulk_g2s(s_P + (size_t)k * nvl, t.PL + (size_t)k * t.p_stride + vbase, 8u * nvl, bar);
+            }
+        }
+        v.xy = s_xy; v.U = s_U; v.P = s_P; v.gid = s_gid; v.cv = s_cv; v.bp = s_bp; v.bins = s_bins;
+        v.u_rows = np2l; v.p_rows = nvl;
+    } else {
+        v.xy = t.coordsL + vbase; v.U = t.UL + dbase; v.P = t.PL + vbase; v.gid = t.gidL + cbase;
+        v.cv = reinterpret_cast<const unsigned *>(t.cvL + 6 * (size_t)cbase);
+        v.bp = t.binptrL + bbase; v.bins = t.binsL + ebase;
+        v.u_rows = (size_t)t.u_stride; v.p_rows = (size_t)t.p_stride;
+    }
     v.x0 = r0.x; v.y0 = r0.y; v.inv_dx = r1.x; v.inv_dy = r1.y; v.gx = i2.z; v.gy = i2.w;
     const double margin = a.tol * (1.0 + 1e-6) + 1e-9;
     // this thread's first record travels while the leaf is being staged
@@ -290,9 +314,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_interp(const TileArgs 
         q = __ldcs(t.rec_xy + b0 + j);
         i = __ldcs(t.rec_id + b0 + j);
     }
-    __syncthreads();  // the barrier is initialised before anyone polls it
+    if (staged) __syncthreads();  // the barrier is initialised before anyone polls it
     if (j >= cnt) return;
-    mbar_wait(bar, 0);
+    if (staged) mbar_wait(bar, 0);
     while (true) {
         tile_locate_eval(a, v, i, q.x, q.y, margin);
         j += blockDim.x;

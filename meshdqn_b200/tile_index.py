@@ -47,7 +47,7 @@ def _pad(n, m):
 class TileIndex:
     __slots__ = ("n_leaves", "depth", "T", "tree", "leaf_info", "leaf_rect", "coordsL", "UL", "PL", "gidL", "cvL",
                  "binptrL", "binsL", "max_nv", "max_np2", "max_nc", "max_nbin", "max_nent", "u_stride", "p_stride",
-                 "leaf_lo", "leaf_hi", "leaf_base", "total_cap")
+                 "leaf_lo", "leaf_hi", "leaf_base", "total_cap", "leaf_bytes", "smem_bytes", "ctas_per_sm")
 
     def nbytes(self):
         return sum(getattr(self, k).nbytes for k in ("tree", "leaf_info", "leaf_rect", "coordsL", "UL", "PL", "gidL",
@@ -62,6 +62,24 @@ class TileIndex:
             right = pts[np.arange(len(pts)), d] >= s
             node = 2 * node + 1 + right
         return node - (self.n_leaves - 1)
+
+
+SM_SMEM_BYTES = 228 * 1024      # shared memory per SM (sm_100a); each resident CTA also costs 1 KB of system-reserved space
+CTA_SMEM_MAX = 227 * 1024
+
+
+def pick_smem(leaf_bytes, mean_points, fit_fraction=0.98):
+    """Dynamic shared memory per CTA of the per-leaf kernel: the highest occupancy class (4, 3, 2, 1 CTAs per SM) in
+    which at least `fit_fraction` of the leaves fit; the kernel serves the remaining (oversize) leaves from HBM.
+    512-thread CTAs (leaves with more than ~288 target points on average, csrc/geom.cu) are register-limited to two
+    per SM.  Returns (bytes, ctas_per_sm) or None when even one CTA per SM does not hold enough leaves."""
+    ks = (4, 3, 2, 1) if mean_points <= 288 else (2, 1)
+    for k in ks:
+        lim = min((SM_SMEM_BYTES // k - 1024) // 16 * 16, CTA_SMEM_MAX)
+        fit = leaf_bytes <= lim
+        if fit.mean() >= fit_fraction:
+            return int(leaf_bytes[fit].max()), k
+    return None
 
 
 def build_tile_index(coords, cells, cell_edges, ne, U0, P0, leaf_cells=256, eps=GRID_EPS, bins_per_cell=4.0,
@@ -241,6 +259,10 @@ def build_tile_index(coords, cells, cell_edges, ne, U0, P0, leaf_cells=256, eps=
     cap = (int(bucket_factor) * own + 32 + 3) // 4 * 4
     ti.leaf_base = np.concatenate([[0], np.cumsum(cap)]).astype(np.int32)
     ti.total_cap = int(ti.leaf_base[-1])
+    # shared memory each leaf's own sections need (csrc/interp_tiled.cuh: tile_leaf_bytes) and the per-CTA allocation
+    ti.leaf_bytes = 16 + 16 * nv_pad + T * (16 * np2_pad + 8 * nv_pad) + 16 * nc_pad + 2 * nbin_pad + 2 * nent_pad
+    picked = pick_smem(ti.leaf_bytes, ti.total_cap / (2.0 * n_leaves))
+    ti.smem_bytes, ti.ctas_per_sm = picked if picked is not None else (0, 0)
     return ti
 
 

@@ -177,7 +177,8 @@ def _coarsened(coords, cells_topo, n_drop, seed, dev):
     return c2, t2, DeviceMesh(c2, t2, dev)
 
 
-@pytest.mark.parametrize("case", ["ys930_leaf64", "synthetic_leaf256", "synthetic_leaf128_overflow", "synthetic_oversized_leaf"])
+@pytest.mark.parametrize("case", ["ys930_leaf64", "synthetic_leaf256", "synthetic_leaf128_overflow", "synthetic_leaf128_hbm_leaves",
+                                  "synthetic_oversized_leaf"])
 def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, case):
     """The tiled (k-d leaf, TMA-staged) kernel must return the same cell ids and the same field bits as the
     uniform-grid kernel, and the oracle's brute-force cell ids."""
@@ -192,7 +193,8 @@ def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, 
     else:
         coords, cells, _ = synthetic_airfoil_mesh(20000, seed=2)
         topo0 = geom.Topology(cells, len(coords))
-        leaf, ndrop = {"synthetic_leaf256": (256, 150), "synthetic_leaf128_overflow": (128, 150)}.get(case, (8192, 150))
+        leaf, ndrop = {"synthetic_leaf256": (256, 150), "synthetic_leaf128_overflow": (128, 150),
+                       "synthetic_leaf128_hbm_leaves": (128, 150)}.get(case, (8192, 150))
     U0, P0 = synthetic_fields(coords, topo0.edges, 5, 1)
     m0 = DeviceMesh(coords, cells, cuda_device)
     if case == "synthetic_oversized_leaf":
@@ -203,6 +205,11 @@ def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, 
     # bucket_factor=0: 32-slot buckets, so most points take the overflow path (served from HBM, same bits)
     tiled = SourceField(m0, U0, P0, tiled=True, leaf_cells=leaf, bucket_factor=0 if case.endswith("overflow") else 2)
     assert tiled.tile is not None and grid.tile is None
+    if case.endswith("hbm_leaves"):
+        # shrink the per-CTA shared memory to the median leaf: half of the leaves no longer fit and are served by
+        # their CTA straight from the leaf arrays in HBM (the route the rare oversize leaf of a graded mesh takes)
+        tiled.tile.smem_bytes = int(np.median(tiled.tile_host.leaf_bytes))
+        assert (tiled.tile_host.leaf_bytes > tiled.tile.smem_bytes).sum() >= 2
     for seed in (0, 1):
         c2, t2, m1 = _coarsened(coords, topo0, ndrop, seed, cuda_device)
         if case == "ys930_leaf64" and seed == 1:
