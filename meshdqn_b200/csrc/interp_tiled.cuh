@@ -34,6 +34,7 @@ struct TileArgs {
     long long u_stride, p_stride;
     int n_leaves, depth;
     int smem_cap;               // dynamic shared memory of this launch; a leaf that needs more is served from HBM
+    int pf_ahead;               // L2 prefetch distance in leaves (CTAs resident on the GPU), 0 = off
     int *leaf_cnt;              // [n_leaves] zero on entry, zero again on exit
     int *ovf_count;             // zero on entry / exit
     unsigned int *ticket;       // zero on entry / exit
@@ -59,6 +60,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                      smem_u32(dst)),
                  "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
 {
@@ -91,31 +96,38 @@ struct LeafView {
     const int *gid;
     const unsigned *cv;             // 3 words per cell: v0|v1, v2|e0, e1|e2
     const unsigned short *bp, *bins;
-    size_t u_rows, p_rows;          // rows between snapshots
+    int u_rows, p_rows;             // rows between snapshots
     double x0, y0, inv_dx, inv_dy;
     int gx, gy;
 };
 
-__device__ __forceinline__ void tile_locate_eval(const InterpArgs &a, const LeafView &v, int i, double px, double py,
-                                                 double margin)
+struct TileHit {
+    int lc;                         // leaf-local cell, -1: no cell contains the point
+    double l0, l1, l2;
+    unsigned w0, w1;                // the cell's first two dof words (v0|v1, v2|e0)
+};
+
+// Point location inside a leaf: the micro-bin's candidates in ascending cell id, first hit = lowest index.
+__device__ __forceinline__ TileHit tile_locate(const LeafView &v, double px, double py, double margin, double tol)
 {
     const int bx = min(max((int)floor((px - v.x0) * v.inv_dx), 0), v.gx - 1);
     const int by = min(max((int)floor((py - v.y0) * v.inv_dy), 0), v.gy - 1);
     const int b = by * v.gx + bx;
     const int s1 = v.bp[b + 1];
     int s = v.bp[b];
-    int lc = -1;
-    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-    unsigned w0 = 0, w1 = 0;
+    TileHit h;
+    h.lc = -1;
+    h.l0 = h.l1 = h.l2 = 0.0;
+    h.w0 = h.w1 = 0;
     while (true) {
         // phase A (division-free): advance to the next candidate the conservative test cannot reject
         double n1 = 0.0, n2 = 0.0, det = 1.0;
         int c = -1;
         while (s < s1) {
             const int cc = v.bins[s++];
-            w0 = v.cv[3 * cc];
-            w1 = v.cv[3 * cc + 1];
-            const double2 A = v.xy[w0 & 0xffffu], B = v.xy[w0 >> 16], C = v.xy[w1 & 0xffffu];
+            h.w0 = v.cv[3 * cc];
+            h.w1 = v.cv[3 * cc + 1];
+            const double2 A = v.xy[h.w0 & 0xffffu], B = v.xy[h.w0 >> 16], C = v.xy[h.w1 & 0xffffu];
             const double d1x = B.x - A.x, d1y = B.y - A.y, d2x = C.x - A.x, d2y = C.y - A.y;
             det = d1x * d2y - d2x * d1y;
             const double qx = px - A.x, qy = py - A.y;
@@ -133,21 +145,28 @@ __device__ __forceinline__ void tile_locate_eval(const InterpArgs &a, const Leaf
         // phase B (the warp reconverges here): the exact test, same operations as bary() in geom.cu.
         // A zero numerator (target point on a source vertex / edge) would take the slow path of the
         // double-precision division; 0 * det has the quotient's value and sign.
-        l1 = n1 == 0.0 ? n1 * det : n1 / det;
-        l2 = n2 == 0.0 ? n2 * det : n2 / det;
-        l0 = 1.0 - l1 - l2;
-        if (fmin(l0, fmin(l1, l2)) >= -a.tol) {
-            lc = c;
+        h.l1 = n1 == 0.0 ? n1 * det : n1 / det;
+        h.l2 = n2 == 0.0 ? n2 * det : n2 / det;
+        h.l0 = 1.0 - h.l1 - h.l2;
+        if (fmin(h.l0, fmin(h.l1, h.l2)) >= -tol) {
+            h.lc = c;
             break;
         }
     }
-    if (lc < 0) {
+    return h;
+}
+
+// P2 velocity / P1 pressure of all T snapshots at the located point (same operation sequence as eval_point in geom.cu)
+__device__ __forceinline__ void tile_eval(const InterpArgs &a, const LeafView &v, int i, const TileHit &h)
+{
+    if (h.lc < 0) {
         a.cell_of[i] = -1;
         a.miss_list[atomicAdd(a.miss_count, 1)] = i;
         return;
     }
-    a.cell_of[i] = v.gid[lc];
-    const unsigned w2 = v.cv[3 * lc + 2];
+    a.cell_of[i] = v.gid[h.lc];
+    const unsigned w2 = v.cv[3 * h.lc + 2];
+    const double l0 = h.l0, l1 = h.l1, l2 = h.l2;
     double phi[6];
     phi[0] = l0 * (2.0 * l0 - 1.0);
     phi[1] = l1 * (2.0 * l1 - 1.0);
@@ -155,12 +174,14 @@ __device__ __forceinline__ void tile_locate_eval(const InterpArgs &a, const Leaf
     phi[3] = 4.0 * l1 * l2;
     phi[4] = 4.0 * l0 * l2;
     phi[5] = 4.0 * l0 * l1;
-    const int dof[6] = {(int)(w0 & 0xffffu), (int)(w0 >> 16), (int)(w1 & 0xffffu),
-                        (int)(w1 >> 16),     (int)(w2 & 0xffffu), (int)(w2 >> 16)};
+    const int dof[6] = {(int)(h.w0 & 0xffffu), (int)(h.w0 >> 16), (int)(h.w1 & 0xffffu),
+                        (int)(h.w1 >> 16),     (int)(w2 & 0xffffu),   (int)(w2 >> 16)};
     const double lam[3] = {l0, l1, l2};
     const int np2t = a.nv + a.ne;
+    double2 *Uo = reinterpret_cast<double2 *>(a.U) + i;
+    double *Po = a.P + i;
     for (int k = 0; k < a.T; ++k) {
-        const double2 *Uk = v.U + (size_t)k * v.u_rows;
+        const double2 *Uk = v.U + k * v.u_rows;
         const double2 u0 = Uk[dof[0]];
         double ux = phi[0] * u0.x, uy = phi[0] * u0.y;   // == 0.0 + phi*u of the reference loop
 #pragma unroll
@@ -169,13 +190,15 @@ __device__ __forceinline__ void tile_locate_eval(const InterpArgs &a, const Leaf
             ux += phi[q] * u.x;
             uy += phi[q] * u.y;
         }
-        __stcs(reinterpret_cast<double2 *>(a.U) + (size_t)k * np2t + i, make_double2(ux, uy));
+        __stcs(Uo, make_double2(ux, uy));
+        Uo += np2t;
         if (i < a.nv) {
-            const double *Pk = v.P + (size_t)k * v.p_rows;
+            const double *Pk = v.P + k * v.p_rows;
             double pv = lam[0] * Pk[dof[0]];
 #pragma unroll
             for (int q = 1; q < 3; ++q) pv += lam[q] * Pk[dof[q]];
-            __stcs(a.P + (size_t)k * a.nv + i, pv);
+            __stcs(Po, pv);
+            Po += a.nv;
         }
     }
 }
@@ -273,38 +296,6 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_interp(const TileArgs t)
     // for the typical leaf (four CTAs per SM) and not for the largest one; the rare leaf that does not fit
     // (large cells overlapping many leaves) is served by this CTA straight from the leaf arrays in HBM.
     const bool staged = tile_leaf_bytes(nvl, np2l, ncl, nbin, nent, T) <= (unsigned)t.smem_cap;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
-    LeafView v;
-    if (staged) {
-        double2 *s_xy = reinterpret_cast<double2 *>(smem + 16);
-        double2 *s_U = s_xy + nvl;
-        double *s_P = reinterpret_cast<double *>(s_U + (size_t)np2l * T);
-        int *s_gid = reinterpret_cast<int *>(s_P + (size_t)nvl * T);
-        unsigned *s_cv = reinterpret_cast<unsigned *>(s_gid + ncl);
-        unsigned short *s_bp = reinterpret_cast<unsigned short *>(s_cv + 3 * ncl);
-        unsigned short *s_bins = s_bp + nbin;
-        if (threadIdx.x == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, tile_leaf_bytes(nvl, np2l, ncl, nbin, nent, T) - 16u);
-            bulk_g2s(s_bp, t.binptrL + bbase, 2u * nbin, bar);
-            bulk_g2s(s_bins, t.binsL + ebase, 2u * nent, bar);
-            bulk_g2s(s_cv, t.cvL + 6 * (size_t)cbase, 12u * ncl, bar);
-            bulk_g2s(s_xy, t.coordsL + vbase, 16u * nvl, bar);
-            bulk_g2s(s_gid, t.gidL + cbase, 4u * ncl, bar);
-            for (int k = 0; k < T; ++k) {
-                bulk_g2s(s_U + (size_t)k * np2l, t.UL + (size_t)k * t.u_stride + dbase, 16u * np2l, bar);
-                bulk_g2s(s_P + (size_t)k * nvl, t.PL + (size_t)k * t.p_stride + vbase, 8u * nvl, bar);
-            }
-        }
-        v.xy = s_xy; v.U = s_U; v.P = s_P; v.gid = s_gid; v.cv = s_cv; v.bp = s_bp; v.bins = s_bins;
-        v.u_rows = np2l; v.p_rows = nvl;
-    } else {
-        v.xy = t.coordsL + vbase; v.U = t.UL + dbase; v.P = t.PL + vbase; v.gid = t.gidL + cbase;
-        v.cv = reinterpret_cast<const unsigned *>(t.cvL + 6 * (size_t)cbase);
-        v.bp = t.binptrL + bbase; v.bins = t.binsL + ebase;
-        v.u_rows = (size_t)t.u_stride; v.p_rows = (size_t)t.p_stride;
-    }
-    v.x0 = r0.x; v.y0 = r0.y; v.inv_dx = r1.x; v.inv_dy = r1.y; v.gx = i2.z; v.gy = i2.w;
     const double margin = a.tol * (1.0 + 1e-6) + 1e-9;
     // this thread's first record travels while the leaf is being staged
     int j = (int)threadIdx.x;
@@ -314,15 +305,87 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_interp(const TileArgs t)
         q = __ldcs(t.rec_xy + b0 + j);
         i = __ldcs(t.rec_id + b0 + j);
     }
-    if (staged) __syncthreads();  // the barrier is initialised before anyone polls it
-    if (j >= cnt) return;
-    if (staged) mbar_wait(bar, 0);
-    while (true) {
-        tile_locate_eval(a, v, i, q.x, q.y, margin);
-        j += blockDim.x;
-        if (j >= cnt) break;
-        q = __ldcs(t.rec_xy + b0 + j);
-        i = __ldcs(t.rec_id + b0 + j);
+    LeafView v;
+    v.x0 = r0.x; v.y0 = r0.y; v.inv_dx = r1.x; v.inv_dy = r1.y; v.gx = i2.z; v.gy = i2.w;
+    // two call sites on purpose: in the staged one every pointer of the view derives from `smem`, so the gathers
+    // compile to LDS with 32-bit addresses instead of generic loads
+    if (staged) {
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+        double2 *s_xy = reinterpret_cast<double2 *>(smem + 16);
+        double2 *s_U = s_xy + nvl;
+        double *s_P = reinterpret_cast<double *>(s_U + np2l * T);
+        int *s_gid = reinterpret_cast<int *>(s_P + nvl * T);
+        unsigned *s_cv = reinterpret_cast<unsigned *>(s_gid + ncl);
+        unsigned short *s_bp = reinterpret_cast<unsigned short *>(s_cv + 3 * ncl);
+        unsigned short *s_bins = s_bp + nbin;
+        if (threadIdx.x == 0) {
+            // two transactions: what point location needs lands first (bar[0]), the coefficients follow (bar[1]) while
+            // the threads are already walking their candidates
+            mbar_init(bar, 1);
+            mbar_init(bar + 1, 1);
+            mbar_expect_tx(bar, 16u * nvl + 12u * ncl + 2u * nbin + 2u * nent);
+            bulk_g2s(s_bp, t.binptrL + bbase, 2u * nbin, bar);
+            bulk_g2s(s_bins, t.binsL + ebase, 2u * nent, bar);
+            bulk_g2s(s_cv, t.cvL + 6 * (size_t)cbase, 12u * ncl, bar);
+            bulk_g2s(s_xy, t.coordsL + vbase, 16u * nvl, bar);
+            mbar_expect_tx(bar + 1, (unsigned)T * (16u * np2l + 8u * nvl) + 4u * ncl);
+            bulk_g2s(s_gid, t.gidL + cbase, 4u * ncl, bar + 1);
+            for (int k = 0; k < T; ++k) {
+                bulk_g2s(s_U + k * np2l, t.UL + (size_t)k * t.u_stride + dbase, 16u * np2l, bar + 1);
+                bulk_g2s(s_P + k * nvl, t.PL + (size_t)k * t.p_stride + vbase, 8u * nvl, bar + 1);
+            }
+        }
+        v.xy = s_xy; v.U = s_U; v.P = s_P; v.gid = s_gid; v.cv = s_cv; v.bp = s_bp; v.bins = s_bins;
+        v.u_rows = np2l; v.p_rows = nvl;
+        if (threadIdx.x == 64 && t.pf_ahead > 0) {
+            // software pipelining across CTAs through L2: ask for the sections of the leaf that the CTA taking this
+            // SM slot next (blockIdx + resident CTAs) will stage, so its bulk copies hit L2 instead of paying the HBM
+            // latency inside its own short life; that CTA's descriptor row is fetched here, off everybody's critical path
+            const int Ln = L + t.pf_ahead;
+            if (Ln < t.n_leaves) {
+                const int4 *inf = reinterpret_cast<const int4 *>(t.leaf_info + 16 * Ln);
+                const int4 n0 = __ldg(inf), n1 = __ldg(inf + 1), n2 = __ldg(inf + 2);
+                bulk_prefetch_l2(t.binptrL + n1.z, 2u * n1.w);
+                bulk_prefetch_l2(t.binsL + n2.x, 2u * n2.y);
+                bulk_prefetch_l2(t.cvL + 6 * (size_t)n1.x, 12u * n1.y);
+                bulk_prefetch_l2(t.coordsL + n0.x, 16u * n0.y);
+                bulk_prefetch_l2(t.gidL + n1.x, 4u * n1.y);
+                for (int k = 0; k < T; ++k) {
+                    bulk_prefetch_l2(t.UL + (size_t)k * t.u_stride + n0.z, 16u * n0.w);
+                    bulk_prefetch_l2(t.PL + (size_t)k * t.p_stride + n0.x, 8u * n0.y);
+                }
+            }
+            if (Ln + t.pf_ahead < t.n_leaves) {   // and the descriptor / counters of the one after that
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(t.leaf_info + 16 * (Ln + t.pf_ahead)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(t.leaf_rect + 4 * (Ln + t.pf_ahead)));
+            }
+        }
+        __syncthreads();  // the barriers are initialised before anyone polls them
+        if (j >= cnt) return;
+        mbar_wait(bar, 0);
+        bool first = true;
+        while (true) {
+            const TileHit h = tile_locate(v, q.x, q.y, margin, a.tol);
+            if (first) { mbar_wait(bar + 1, 0); first = false; }
+            tile_eval(a, v, i, h);
+            j += blockDim.x;
+            if (j >= cnt) break;
+            q = __ldcs(t.rec_xy + b0 + j);
+            i = __ldcs(t.rec_id + b0 + j);
+        }
+    } else {
+        v.xy = t.coordsL + vbase; v.U = t.UL + dbase; v.P = t.PL + vbase; v.gid = t.gidL + cbase;
+        v.cv = reinterpret_cast<const unsigned *>(t.cvL + 6 * (size_t)cbase);
+        v.bp = t.binptrL + bbase; v.bins = t.binsL + ebase;
+        v.u_rows = (int)t.u_stride; v.p_rows = (int)t.p_stride;
+        if (j >= cnt) return;
+        while (true) {
+            tile_eval(a, v, i, tile_locate(v, q.x, q.y, margin, a.tol));
+            j += blockDim.x;
+            if (j >= cnt) break;
+            q = __ldcs(t.rec_xy + b0 + j);
+            i = __ldcs(t.rec_id + b0 + j);
+        }
     }
 }
 
@@ -345,10 +408,10 @@ __global__ void __launch_bounds__(256) k_tile_overflow(const TileArgs t)
         v.xy = t.coordsL + info[0]; v.U = t.UL + info[2]; v.P = t.PL + info[0]; v.gid = t.gidL + info[4];
         v.cv = reinterpret_cast<const unsigned *>(t.cvL + 6 * (size_t)info[4]);
         v.bp = t.binptrL + info[6]; v.bins = t.binsL + info[8];
-        v.u_rows = (size_t)t.u_stride; v.p_rows = (size_t)t.p_stride;
+        v.u_rows = (int)t.u_stride; v.p_rows = (int)t.p_stride;
         v.x0 = t.leaf_rect[4 * L]; v.y0 = t.leaf_rect[4 * L + 1]; v.inv_dx = t.leaf_rect[4 * L + 2];
         v.inv_dy = t.leaf_rect[4 * L + 3]; v.gx = info[10]; v.gy = info[11];
-        tile_locate_eval(a, v, i, px, py, margin);
+        tile_eval(a, v, i, tile_locate(v, px, py, margin, a.tol));
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -42,6 +42,8 @@ def main():
         leafs = [int(x) for x in os.environ.get("LEAF_CELLS", "256,128").split(",")]
         for name, kw in [("grid", dict(tiled=False))] + [(f"tiled{k}", dict(tiled=True, leaf_cells=k)) for k in leafs]:
             t0 = time.time()
+            if kw["tiled"] and os.environ.get("MICRO_BINS"):
+                kw = dict(kw, micro_bins_per_cell=float(os.environ["MICRO_BINS"]))
             src = SourceField(m0, U0, P0, **kw)
             tb = time.time() - t0
             out = src.interpolate(m2)
