@@ -292,6 +292,14 @@ def run_ours(args):
     trainer.timers = None
     clk.__exit__()
 
+    # extras: the single-GPU secondary numbers run at N = 1 only; at N > 1 the one extra with a collective (the
+    # sharded candidate batch, BASELINE.json configs[4]) runs on EVERY rank -- never inside the rank-0 block
+    extras = {}
+    if not args.no_extras:
+        if world == 1:
+            extras = measure_extras(dev, nets[0], rb_dev, flush, args)
+        else:
+            extras = {"candidate_batch": bench_candidates(nets[0], rb_dev, dev, rank, world, flush)}
     line = None
     if rank == 0:
         hbm, how = peaks()
@@ -304,9 +312,6 @@ def run_ours(args):
         dom = "qnet_bwd+wgrad"
         dom_us = kern.get(dom, float("nan"))
         achieved = alg_bytes / (dom_us * 1e-6) / 1e9
-        extras = {}
-        if not args.no_extras:
-            extras = measure_extras(dev, nets[0], rb_dev, flush, args)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(world), **({"setup": "fast-setup: random graphs (profiling run, not a bench value)"} if args.fast_setup else {})),

@@ -17,7 +17,6 @@
 // One graph per call (B = 1); every size the launches need is known on the host (n_{l+1} = ceil(ratio * n_l) in
 // float32, as PyG computes it), edge counts stay on the device.  No host synchronisation inside.
 #include <math.h>
-#include <stdlib.h>
 
 #include <algorithm>
 
@@ -211,6 +210,11 @@ __global__ void k_csr_sort_rows(const int *__restrict__ src, const int *__restri
 // Each output element is summed sequentially in CSR (= edge) order, so the bits equal torch_scatter's CPU loop;
 // no atomics, deterministic.
 // (32-bit index arithmetic throughout: a 64-bit division per thread costs more instructions than the kernel's work)
+// Two alternatives were measured on the 0.5M-node / 3.0M-edge graph and dropped (ncu, same bits): a single-pass
+// shared-memory tile kernel with one thread per (row, feature) reading the unpadded rows -- 87 us, issue-bound at
+// 50 M warp instructions (one LDG + FADD per lane and edge) against 72 us for this pair (19 + 53, 35 M); and a
+// thread-per-row kernel with the row in registers -- 11.6 M instructions but 61 us after the same pad pass, bound
+// by the L1 sector rate of fully divergent 16-byte loads (32 rows per request, l1tex 60 %).
 template <int CH>   // CH > 0: compile-time chunks per row (constant division), 0: runtime
 __global__ void __launch_bounds__(256) k_pad_rows(const float *__restrict__ X, int ldx, int col0, int F, int n_rows, int ch_rt,
                                                   float *__restrict__ A, int lda)
@@ -264,112 +268,6 @@ __global__ void __launch_bounds__(256) k_sage_rows_vec4(const int *__restrict__ 
         // columns beyond 2 Fp (lda rounded up for the tensor-core K step) are zeroed by the chunk-0 thread
         if (c == 0)
             for (int k = 8 * ch; k < lda; ++k) A[(size_t)r * lda + k] = 0.f;
-    }
-}
-
-// Narrow rows, thread per ROW (the default after k_pad_rows): the whole padded feature row lives in registers
-// (CH float4 accumulators), so every instruction of the edge loop does useful work on all 32 lanes -- per edge and
-// lane: one col load, CH LDG.128 of the neighbour's 16-byte-aligned left half, 4 CH FADD -- about a tenth of the
-// warp instructions the (row, chunk)-per-thread kernel issues for the same sums.  Lanes read different rows, so a
-// request touches 32 sectors; the CH consecutive chunk loads of a lane share its row's three sectors (L1), and mesh
-// neighbours of consecutive rows overlap, so most of the sector traffic stays in L1/L2.  Two neighbours in flight.
-// Sums are sequential in CSR (= edge) order per element, as in every other variant (same bits).
-template <int CH>
-__global__ void __launch_bounds__(128) k_sage_rows_thread(const int *__restrict__ row_ptr, const int *__restrict__ col,
-                                                          int n_rows, float *__restrict__ A, int lda)
-{
-    const unsigned ld4 = (unsigned)lda >> 2;
-    const float4 *A4 = reinterpret_cast<const float4 *>(A);
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        const int a = __ldg(row_ptr + r), b = __ldg(row_ptr + r + 1);
-        float4 s[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) s[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int e = a;
-        for (; e + 2 <= b; e += 2) {
-            const unsigned j0 = __ldg(col + e), j1 = __ldg(col + e + 1);
-            const float4 *p0 = A4 + (size_t)j0 * ld4, *p1 = A4 + (size_t)j1 * ld4;
-            float4 v0[CH], v1[CH];
-#pragma unroll
-            for (int c = 0; c < CH; ++c) v0[c] = p0[c];     // plain loads: the left half of A was written by k_pad_rows
-#pragma unroll
-            for (int c = 0; c < CH; ++c) v1[c] = p1[c];
-#pragma unroll
-            for (int c = 0; c < CH; ++c) { s[c].x += v0[c].x; s[c].y += v0[c].y; s[c].z += v0[c].z; s[c].w += v0[c].w; }
-#pragma unroll
-            for (int c = 0; c < CH; ++c) { s[c].x += v1[c].x; s[c].y += v1[c].y; s[c].z += v1[c].z; s[c].w += v1[c].w; }
-        }
-        if (e < b) {
-            const float4 *p0 = A4 + (size_t)(unsigned)__ldg(col + e) * ld4;
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const float4 v = p0[c];
-                s[c].x += v.x; s[c].y += v.y; s[c].z += v.z; s[c].w += v.w;
-            }
-        }
-        const float deg = (float)max(b - a, 1);
-        float4 *out = reinterpret_cast<float4 *>(A + (size_t)r * lda) + CH;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) out[c] = make_float4(s[c].x / deg, s[c].y / deg, s[c].z / deg, s[c].w / deg);
-        for (int k = 8 * CH; k < lda; ++k) A[(size_t)r * lda + k] = 0.f;   // columns beyond 2 Fp (K-step round-up)
-    }
-}
-
-// Narrow rows in ONE pass (the default): a CTA owns RB consecutive output rows and builds their [x | mean | 0-pad]
-// GEMM-operand rows in shared memory, then writes the tile as one contiguous block of float4 (rows are consecutive,
-// so RB*lda floats are contiguous in A: every store is a full, coalesced 512-byte warp request; no partial sectors,
-// no second pass over A).  The tile's CSR slice (row_ptr and the col entries of its rows, contiguous in memory) is
-// staged in shared memory first, so the gather phase has a single level of global-memory latency: thread per
-// (row, real feature), consecutive lanes read consecutive floats of a neighbour's unpadded 4F-byte row, four neighbour
-// loads in flight per thread, summed sequentially in CSR (= edge) order as torch_scatter's CPU loop does.
-constexpr int ST_RB = 128;      // rows per tile
-constexpr int ST_ECAP = 2048;   // staged col entries per tile (mean degree <= 16); larger tiles read col from global memory
-template <int CH, int FT>   // CH > 0: compile-time chunks per row and feature count FT (constant divisions); 0: runtime
-__global__ void __launch_bounds__(256) k_sage_rows_tile(const float *__restrict__ X, int ldx, int col0, int F,
-                                                        const int *__restrict__ row_ptr, const int *__restrict__ col,
-                                                        int n_rows, int ch_rt, float *__restrict__ A, int lda)
-{
-    extern __shared__ float4 st_smem4[];
-    float *tile = reinterpret_cast<float *>(st_smem4);              // [ST_RB][lda]
-    int *s_rp = reinterpret_cast<int *>(tile + ST_RB * lda);        // [ST_RB + 1]
-    int *s_col = s_rp + ST_RB + 4;                                  // [ST_ECAP]
-    const int Fp = 4 * (CH > 0 ? CH : ch_rt);
-    const int tid = threadIdx.x;
-    for (int r0 = blockIdx.x * ST_RB; r0 < n_rows; r0 += gridDim.x * ST_RB) {
-        const int nr = min(ST_RB, n_rows - r0);
-        for (int i = tid; i <= nr; i += 256) s_rp[i] = __ldg(row_ptr + r0 + i);
-        __syncthreads();
-        const int e0 = s_rp[0], ne = s_rp[nr] - e0;
-        const bool staged = ne <= ST_ECAP;
-        if (staged)
-            for (int i = tid; i < ne; i += 256) s_col[i] = __ldg(col + e0 + i);
-        const int npad = lda - 2 * F, padl = Fp - F;                 // zero columns: [F, Fp) and [Fp + F, lda)
-        for (int i = tid; i < nr * npad; i += 256) {
-            const int r = i / npad, c = i - r * npad;
-            tile[r * lda + (c < padl ? F + c : Fp + F + (c - padl))] = 0.f;
-        }
-        __syncthreads();
-        // thread per (row, REAL feature): no idle pad lanes, one LDS + one IMAD + one LDG + one FADD per edge
-        const unsigned nf = (unsigned)(CH > 0 ? FT : F);
-        for (unsigned idx = tid; idx < (unsigned)nr * nf; idx += 256) {
-            const unsigned r = idx / nf, f = idx - r * nf;
-            const float *Xf = X + col0 + f;
-            const int a = s_rp[r] - e0, b = s_rp[r + 1] - e0;
-            float s = 0.f;
-            if (staged) {
-#pragma unroll 4
-                for (int e = a; e < b; ++e) s += __ldg(Xf + (unsigned)s_col[e] * (unsigned)ldx);
-            } else {
-                for (int e = a; e < b; ++e) s += __ldg(Xf + (unsigned)__ldg(col + e0 + e) * (unsigned)ldx);
-            }
-            tile[r * lda + f] = __ldg(Xf + (unsigned)(r0 + r) * (unsigned)ldx);
-            tile[r * lda + Fp + f] = s / (float)max(b - a, 1);
-        }
-        __syncthreads();
-        float4 *dst = reinterpret_cast<float4 *>(A + (size_t)r0 * lda);
-        const int n4 = nr * (lda >> 2);
-        for (int i = tid; i < n4; i += 256) dst[i] = st_smem4[i];
-        __syncthreads();
     }
 }
 
@@ -1036,34 +934,6 @@ int sage_rows(const float *X, int ldx, int col0, int F, const int *row_ptr, cons
             return MDQ_EINVAL;
         }
         int rc;
-        // variants kept for A/B timing (MDQ_SAGE_MODE = thread | vec4 | tile); all return the same bits
-        static const char *mode_env = getenv("MDQ_SAGE_MODE");
-        const int mode = !mode_env ? 0 : (mode_env[0] == 'v' ? 1 : (mode_env[0] == 't' && mode_env[1] == 'i' ? 2 : 0));
-        const size_t tile_bytes = sizeof(float) * (size_t)ST_RB * lda + sizeof(int) * (ST_RB + 4 + ST_ECAP);
-        if (mode == 2 && tile_bytes <= 48 * 1024 && (long long)n * ldx < (1LL << 32)) {
-            const int gridt = grid_for(n, ST_RB, 148 * 8);
-            if (ch == 5 && F == 17) k_sage_rows_tile<5, 17><<<gridt, 256, tile_bytes, st>>>(X, ldx, col0, F, row_ptr, col, n, ch, A, lda);
-            else k_sage_rows_tile<0, 0><<<gridt, 256, tile_bytes, st>>>(X, ldx, col0, F, row_ptr, col, n, ch, A, lda);
-            return mdq::check_launch("k_sage_rows_tile");
-        }
-        if (mode == 0 && ch <= 8) {
-            const int gridp = grid_for((long long)n * ch, 256, 148 * 64);
-            if (ch == 5) k_pad_rows<5><<<gridp, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);
-            else k_pad_rows<0><<<gridp, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);
-            if ((rc = mdq::check_launch("k_pad_rows"))) return rc;
-            const int gridr = grid_for(n, 128, 148 * 10);   // 50 registers x 128 threads: ten CTAs per SM
-            switch (ch) {
-            case 1: k_sage_rows_thread<1><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            case 2: k_sage_rows_thread<2><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            case 3: k_sage_rows_thread<3><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            case 4: k_sage_rows_thread<4><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            case 5: k_sage_rows_thread<5><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            case 6: k_sage_rows_thread<6><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            case 7: k_sage_rows_thread<7><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            default: k_sage_rows_thread<8><<<gridr, 128, 0, st>>>(row_ptr, col, n, A, lda); break;
-            }
-            return mdq::check_launch("k_sage_rows_thread");
-        }
         const int grid = grid_for((long long)n * ch, 256, 148 * 64);
         if (ch == 5) k_pad_rows<5><<<grid, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);
         else k_pad_rows<0><<<grid, 256, 0, st>>>(X, ldx, col0, F, n, ch, A, lda);

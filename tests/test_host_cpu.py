@@ -127,3 +127,29 @@ def test_synthetic_mesh_generator():
     # (Env2DAirfoil.py:496) also drops just outside a concave stretch of the contour
     assert abs(int((tags == 1).sum()) - n_ring) <= 3
     assert len(coords) - topo.ne + len(cells) == 0
+
+
+def test_replay_batch_arena_packing_round_trip(monkeypatch):
+    """ReplayBatch.pin_memory packs the whole minibatch into one arena; the views must equal the collated tensors
+    and survive `.to()` (one copy) with the kernel-facing metadata intact."""
+    import torch
+    from meshdqn_b200.data import Data
+    from meshdqn_b200.replay import ReplayBatch
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)      # no CUDA driver in the CPU suite
+    g = torch.Generator().manual_seed(5)
+    mk = lambda n, e: Data(x=torch.randn(n, 17, generator=g), edge_index=torch.randint(0, n, (2, e), generator=g))
+    tr = [(mk(180, 372), 3, mk(179, 370), 0.5), (mk(150, 300), 180, None, -1.0), (mk(7, 0), 0, mk(6, 2), 0.25)]
+    rb = ReplayBatch.from_transitions(tr)
+    rp = rb.pin_memory()
+    assert rp._arena is not None and rp._arena.numel() % 256 == 0 and rp.h2d_bytes() == rp._arena.numel()
+    for rr in (rp, rp.to("cpu")):
+        for k in ("actions", "next_slot", "rewards", "owner"):
+            assert torch.equal(getattr(rr, k), getattr(rb, k))
+        for name in ("states", "next_states"):
+            a, b = getattr(rr, name), getattr(rb, name)
+            for k in ("x", "edge_index", "batch", "ptr", "eptr"):
+                assert torch.equal(getattr(a, k), getattr(b, k)) and getattr(a, k).dtype == getattr(b, k).dtype
+            m, m0 = a._host_meta(), b._host_meta()
+            assert torch.equal(m[0], m0[0]) and torch.equal(m[1], m0[1]) and m[2:] == m0[2:]
+            assert a.edge_index.data_ptr() % 16 == 0 and a.x.data_ptr() % 16 == 0
+        assert rr.tensors()[0] is rr._arena and len(rr.tensors()) == 1
