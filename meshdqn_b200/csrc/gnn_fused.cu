@@ -60,6 +60,7 @@ struct WDesc {
     int nl;
     int total;  // floats of workspace
     WLayer l[MAXWL];
+    int tstart[MAXWL + 1];  // weight-gradient tasks of layer i are [tstart[i], tstart[i+1]) (filled at launch)
 };
 
 struct QArgs {
@@ -1356,7 +1357,8 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
 // ------------------------------------------------------------------------------------------------
 // weight gradient: partial[s][k][c] = sum_{rows in chunk s} in[row][k] * delta[row][c]   (k == K -> bias)
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_ROWS = 128;  // rows per chunk
+constexpr int WG_ROWS = 32;   // rows per chunk: short dependent-load chains (the kernel is latency-, not FLOP-bound: ~0.1 GFLOP),
+                              // the chunk partials are summed in fixed order by wgrad_reduce_kernel
 constexpr int WG_KG = 8;      // k values per thread
 
 // layer li: S chunks of WG_ROWS rows, nkg groups of WG_KG k-values; partial offset = sum over earlier layers
@@ -1377,14 +1379,19 @@ __device__ __forceinline__ void wg_layer_geom(const WDesc &wd, int B, int li, in
 __global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int B, const float *__restrict__ ws,
                                                             float *__restrict__ partial)
 {
-    __shared__ __align__(16) float xin[WG_ROWS][WG_KG];  // the chunk's input rows, these WG_KG k-values (4 KB)
-    const int li = blockIdx.y;
+    __shared__ __align__(16) float xin[WG_ROWS][WG_KG];  // the chunk's input rows, these WG_KG k-values
+    // one CTA per task, tasks of all layers flattened (a 2-D grid sized by the largest layer launched ~5x more CTAs
+    // than there are tasks, and their scheduling alone cost more than the arithmetic)
+    int li = 0;
+    while (li + 1 < wd.nl && (int)blockIdx.x >= wd.tstart[li + 1]) ++li;
     const WLayer l = wd.l[li];
     if (l.rpg == 0) return;
     int S, nkg, poff;
     wg_layer_geom(wd, B, li, S, nkg, poff);
     const int KB = l.K + 1;  // last "k" is the bias column (input == 1)
-    for (int t = blockIdx.x; t < S * nkg; t += gridDim.x) {
+    {
+        const int t = (int)blockIdx.x - wd.tstart[li];
+        if (t >= S * nkg) return;
         const int kg = t / S, chunk = t - kg * S;
         const int rows = B * l.rpg;
         const int r0 = chunk * WG_ROWS, r1 = min(rows, r0 + WG_ROWS);
@@ -1405,7 +1412,7 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int 
             for (int j = 0; j < WG_KG; ++j) acc[j] = 0.f;
             const float *dl = ws + l.d_off + c;
             const int nr = r1 - r0;
-#pragma unroll 4
+#pragma unroll 8
             for (int rr = 0; rr < nr; ++rr) {
                 const float d = __ldg(dl + (size_t)(r0 + rr) * l.C);
                 const float4 xa = *reinterpret_cast<const float4 *>(&xin[rr][0]);
@@ -1437,7 +1444,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WDesc wd, int B
         const int k = idx / l.C, c = idx - k * l.C;
         const int kg = k / WG_KG, kj = k - kg * WG_KG;
         float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += pl[((size_t)(kg * S + s) * WG_KG + kj) * l.C + c];
+        const float *pp = pl + ((size_t)kg * S * WG_KG + kj) * l.C + c;
+        const size_t sstep = (size_t)WG_KG * l.C;
+#pragma unroll 8
+        for (int s = 0; s < S; ++s) acc += __ldg(pp + s * sstep);   // independent loads, fixed summation order
         if (k < l.K) {
             if (l.w_off >= 0) grad[l.w_off + (size_t)k * l.C + c] = acc;
         } else if (l.b_off >= 0) {
@@ -1686,25 +1696,26 @@ static int qnet_backward_launch(const mdq_net_t *net, const float *params, const
     a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
     a.B = n_graphs; a.ws = workspace; a.trace = g_trace;
     const WDesc &wd = a.wd;
-    int max_tasks = 1;
+    int n_tasks = 0;
     for (int i = 0; i < wd.nl; ++i) {
         const WLayer &l = wd.l[i];
+        a.wd.tstart[i] = n_tasks;
         if (l.rpg == 0) continue;
         const int S = (n_graphs * l.rpg + WG_ROWS - 1) / WG_ROWS;
         const int nkg = (l.K + 1 + WG_KG - 1) / WG_KG;
-        if (S * nkg > max_tasks) max_tasks = S * nkg;
+        n_tasks += S * nkg;
     }
+    a.wd.tstart[wd.nl] = n_tasks;
     float *d_partial = workspace + wd.total;
     cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net->n_params * sizeof(float), st);
     if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
     qnet_kernel<true><<<n_graphs, NT, (size_t)a.L.total * 4, st>>>(a);
     rc = mdq::check_launch("qnet_kernel<bwd>");
     if (rc != MDQ_OK) return rc;
-    dim3 pg(max_tasks, wd.nl);
-    wgrad_partial_kernel<<<pg, 256, 0, st>>>(a.wd, n_graphs, workspace, d_partial);
+    wgrad_partial_kernel<<<n_tasks > 0 ? n_tasks : 1, 256, 0, st>>>(a.wd, n_graphs, workspace, d_partial);
     rc = mdq::check_launch("wgrad_partial_kernel");
     if (rc != MDQ_OK) return rc;
-    dim3 rg(16, wd.nl);
+    dim3 rg(32, wd.nl);
     wgrad_reduce_kernel<<<rg, 256, 0, st>>>(a.wd, n_graphs, d_partial, grad);
     return mdq::check_launch("wgrad_reduce_kernel");
 }
