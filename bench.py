@@ -9,7 +9,7 @@ gradient all-reduce (NCCL, N>1), Adam.  A "step" is one such replay step; `value
 ReplayBatch.to(device) from pinned host memory plus the loss read-back every step.
 Extras on the same JSON line: forward-only Q-evals, ys930 env steps, re-interpolation vertices/s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--big]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--small]
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 --impl reference times the CPU oracle restatement of the same replay step on the host cores (the
@@ -319,7 +319,10 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rb_host.h2d_bytes()), "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "qnet_kernel<bwd> + wgrad_partial + wgrad_reduce", "achieved": achieved,
-                             "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                             "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm,
+                             # dram__bytes_read+write per launch of the group from one `ncu --set full` capture (cold caches):
+                             # qnet_kernel<bwd> 5.62 MB + wgrad_partial 6.20 MB + wgrad_reduce 8.00 MB (profiles/r01_ncu_raw_qnet_replay.txt)
+                             "traffic": 19822336,
                              "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": dom_us,
                              "note": "launch/latency-bound at 256 x 180-node graphs (15 KB per graph); see DESIGN.md"},
                 "kernel_us": kern, "extras": extras}
@@ -436,7 +439,7 @@ def measure_extras(dev, net, rb_dev, flush, args):
     npt = m1.nv + m1.ne
     out["reinterp_ys930"] = {"vertices_per_s": npt / (ms * 1e-3), "us_per_launch": ms * 1e3, "target_points": npt, "T": 5}
     # large synthetic mesh: full-field re-interpolation onto a coarsened copy (throughput mode, no smoothing)
-    ntri = 1_000_000 if args.big else 250_000
+    ntri = 250_000 if args.small else 1_000_000   # BASELINE.json configs[3] names the ~1M-triangle mesh
     coords, cells, _ = synthetic_airfoil_mesh(ntri, seed=0, order="morton")
     m0 = DeviceMesh(coords, cells, dev)
     U0, P0 = synthetic_fields(coords, m0.edges.cpu().numpy(), 5, 0)
@@ -549,7 +552,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--big", action="store_true", help="use the ~1M-triangle synthetic mesh for the re-interpolation extra")
+    ap.add_argument("--small", action="store_true", help="250k-triangle synthetic mesh for the large-mesh extras (default: the ~1M-triangle mesh of configs[3])")
+    ap.add_argument("--big", action="store_true", help="(default now) kept for compatibility")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--fast-setup", action="store_true", help="random graphs instead of harvested transitions (profiler runs only)")
     ap.add_argument("--no-cpu", action="store_true")

@@ -304,8 +304,18 @@ __device__ void build_csr(int n, int E, const eid_t *es, const eid_t *ed, int *r
             if (e < E) {
                 const int d = ed[e];
                 int r = 0;
-#pragma unroll 4
-                for (int e2 = 0; e2 < e; ++e2) r += (ed[e2] == d);
+                // eight 16-bit destinations per 16-byte load (ed is 16-byte aligned): xor with d replicated, count
+                // the zero halves -- ~1.5 instructions per earlier edge instead of a dependent LDS per edge
+                const unsigned dd = (unsigned)d * 0x10001u;
+                const uint4 *ed4 = reinterpret_cast<const uint4 *>(ed);
+                const int full = ((reinterpret_cast<uintptr_t>(ed) & 15) == 0) ? (e >> 3) : 0;   // later blocks' lists may start unaligned
+                for (int q = 0; q < full; ++q) {
+                    const uint4 v = ed4[q];
+                    const unsigned x0 = v.x ^ dd, x1 = v.y ^ dd, x2 = v.z ^ dd, x3 = v.w ^ dd;
+                    r += !(x0 & 0xffffu) + !(x0 >> 16) + !(x1 & 0xffffu) + !(x1 >> 16) +
+                         !(x2 & 0xffffu) + !(x2 >> 16) + !(x3 & 0xffffu) + !(x3 >> 16);
+                }
+                for (int e2 = full << 3; e2 < e; ++e2) r += (ed[e2] == d);
                 myrank[it] = r;
                 atomicAdd(&cursor[d], 1);
             }
@@ -530,6 +540,73 @@ struct WStream {
     __device__ __forceinline__ void release(int j) const { stamp(j, 2); }
 };
 
+// Direct-mode dense layer for the small pooled levels (18, 2, 1 rows per graph): out = act(bias + A . WT), WT [K][W]
+// read straight from L2.  A TR x 4 register tile per thread over (row group, column quad) items, and the K range
+// split over KS = NT / items thread slices so that all eight warps issue FMAs (one 4 x 4 tile per thread used 160
+// threads for 18 rows and 32 for <= 4 rows: the phase was bound by the issue rate of the one or two busy schedulers).
+// The slices' partial sums are added into `out` in slice order (fixed, so results are reproducible), bias first.
+template <int TR>
+__device__ void dense_direct(const float *__restrict__ WT, int n, int K, const float *A, int lda, const float *bias,
+                             float *out, int ldo, int W, bool relu)
+{
+    const int q = W >> 2;
+    const int items = ((n + TR - 1) / TR) * q;   // <= NT (caller)
+    const int ks_raw = NT / items;
+    const int KS = ks_raw >= 8 ? 8 : (ks_raw >= 4 ? 4 : (ks_raw >= 2 ? 2 : 1));
+    const int slice = threadIdx.x / items, item = threadIdx.x - slice * items;
+    const bool active = slice < KS;
+    const int rg = active ? item / q : 0;
+    const int c4 = active ? (item - rg * q) << 2 : 0;
+    const int r0 = rg * TR;
+    const int kper = ((K + 4 * KS - 1) / (4 * KS)) * 4;
+    const int k0 = min(K, slice * kper), k1 = active ? min(K, k0 + kper) : k0;
+    const float *a[TR];
+#pragma unroll
+    for (int j = 0; j < TR; ++j) a[j] = A + (size_t)min(r0 + j, n - 1) * lda;
+    float acc[TR][4];
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && active && slice == 0) b4 = __ldg(reinterpret_cast<const float4 *>(bias + c4));
+#pragma unroll
+    for (int j = 0; j < TR; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+    const float *wp = WT + (size_t)k0 * W + c4;
+#pragma unroll 2
+    for (int k = k0; k < k1; k += 4, wp += 4 * (size_t)W) {
+        float4 w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) w[t] = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)t * W));
+#pragma unroll
+        for (int j = 0; j < TR; ++j) {
+            const float4 xv = *reinterpret_cast<const float4 *>(a[j] + k);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                acc[j][0] = fmaf(xs[t], w[t].x, acc[j][0]);
+                acc[j][1] = fmaf(xs[t], w[t].y, acc[j][1]);
+                acc[j][2] = fmaf(xs[t], w[t].z, acc[j][2]);
+                acc[j][3] = fmaf(xs[t], w[t].w, acc[j][3]);
+            }
+        }
+    }
+    for (int s = 0; s < KS; ++s) {
+        if (active && slice == s) {
+#pragma unroll
+            for (int j = 0; j < TR; ++j) {
+                if (r0 + j < n) {
+                    float4 *o = reinterpret_cast<float4 *>(out + (size_t)(r0 + j) * ldo + c4);
+                    float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    if (s > 0) {
+                        const float4 p = *o;
+                        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                    }
+                    if (relu && s == KS - 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    *o = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // out[r][c] = act(bias[c] + sum_k A[r][k] * WT[k][c]) with WT streamed through shared-memory stages.
 // One 4x4 output tile per thread (host guarantees ceil(n/4) * W/4 <= NT); k ascending.
 __device__ void dense_stream(const WStream &ws, int j0, int n, int K, const float *A, int lda, const float *bias, float *out,
@@ -537,6 +614,12 @@ __device__ void dense_stream(const WStream &ws, int j0, int n, int K, const floa
 {
     const int q = W >> 2;
     const int ngroups = (n + 3) >> 2;
+    if (ws.ns == 0 && (K & 3) == 0) {   // direct mode: weights contiguous [K][W] in the parameter buffer
+        const float *WT = ws.params + ws.ck->off[j0];
+        const int g5 = (n + 4) / 5;
+        if (g5 * q * 2 <= NT && ngroups * q * 2 > NT) { dense_direct<5>(WT, n, K, A, lda, bias, out, ldo, W, relu); return; }
+        if (ngroups * q <= NT) { dense_direct<4>(WT, n, K, A, lda, bias, out, ldo, W, relu); return; }
+    }
     const int gpp = NT / q;  // row groups per pass (a second pass only happens in direct mode, ws.ns == 0)
     for (int g0 = 0; g0 < ngroups; g0 += gpp) {
         const int item = threadIdx.x;
@@ -867,14 +950,14 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
         MDQ_TRACE();  // L1: inputs loaded
         build_csr(n, E, e1s, e1d, rowptr, cursor, csr);
         MDQ_TRACE();  // L1: csr
-        for (int i = warp; i < n; i += NWARP) {  // mean aggregation, edge order per row; lanes over features
+        // mean aggregation, edge order per row; thread per (row, feature) so that all 32 lanes work (a warp per row
+        // used 17 of them) and a thread's items are independent chains
+        for (int idx = tid; idx < n * F; idx += NT) {
+            const int i = idx / F, f = idx - i * F;
             const int s0 = rowptr[i], s1 = rowptr[i + 1];
-            const float inv_cnt = (float)(s1 - s0 > 0 ? s1 - s0 : 1);
-            for (int f = lane; f < F; f += 32) {
-                float sum = 0.f;
-                for (int s = s0; s < s1; ++s) sum += cat1[csr[s] * KC1 + F + f];
-                cat1[i * KC1 + f] = sum / inv_cnt;
-            }
+            float sum = 0.f;
+            for (int s = s0; s < s1; ++s) sum += cat1[csr[s] * KC1 + F + f];
+            cat1[i * KC1 + f] = sum / (float)(s1 - s0 > 0 ? s1 - s0 : 1);
         }
         __syncthreads();
         MDQ_TRACE();  // L1: aggregated
@@ -892,19 +975,26 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
         MDQ_TRACE();  // L1: scores
         const int k = topk_count_dev(net.ratio, n);
         const int obase = seg[1 * (G + 1) + gi];
-        for (int i = warp; i < n; i += NWARP) {
+        // rank = number of rows ahead of i in (score desc, index asc) order.  Thread per row, every thread walks all
+        // scores: the reads are shared-memory broadcasts (same address across the warp) and independent, so the loop
+        // is ~4 instructions per j at full ILP instead of a shuffle-reduction chain per row.
+        for (int i = tid; i < n; i += NT) {
             const float si = score[i];
             int r = 0;
-            for (int j = lane; j < n; j += 32) {
+            int j = 0;
+            for (; j + 4 <= n; j += 4) {                       // score[] is 16-byte aligned (shared-memory carve-up)
+                const float4 s4 = *reinterpret_cast<const float4 *>(score + j);
+                r += (s4.x > si) || (s4.x == si && j < i);
+                r += (s4.y > si) || (s4.y == si && j + 1 < i);
+                r += (s4.z > si) || (s4.z == si && j + 2 < i);
+                r += (s4.w > si) || (s4.w == si && j + 3 < i);
+            }
+            for (; j < n; ++j) {
                 const float sj = score[j];
                 r += (sj > si) || (sj == si && j < i);
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
-            if (lane == 0) {
-                newid[i] = (r < k) ? (obase + r) : -1;
-                if (r < k) parent[L.n_max + L.rowoff[1] + obase + r] = i;
-            }
+            newid[i] = (r < k) ? (obase + r) : -1;
+            if (r < k) parent[L.n_max + L.rowoff[1] + obase + r] = i;
         }
         if (tid == 0) seg[1 * (G + 1) + gi + 1] = obase + k;
         __syncthreads();
