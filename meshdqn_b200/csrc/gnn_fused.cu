@@ -1157,7 +1157,9 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
     if (a.emb)
         for (int idx = tid; idx < ng * 2 * W; idx += NT) a.emb[(size_t)g0 * 2 * W + idx] = racc[idx];
     mlp_stream(wst, L.ck_lin[0], ng, net.lin_in[0], net.lin_out[0], racc, 2 * W, P + net.lin_boff[0], y1, YM, true, part);
+    MDQ_TRACE();  // lin1
     mlp_stream(wst, L.ck_lin[1], ng, net.lin_in[1], net.lin_out[1], y1, YM, P + net.lin_boff[1], y2, YM, true, part);
+    MDQ_TRACE();  // lin2
     mlp_stream(wst, L.ck_lin[2], ng, net.lin_in[2], net.lin_out[2], y2, YM, P + net.lin_boff[2], y3, YM, false, part);
     MDQ_TRACE();  // MLP done
     const int A = net.out_dim;
@@ -1298,10 +1300,13 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
             }
         }
         __syncthreads();
+        MDQ_TRACE();  // backward: Huber / softmax gradient
         emit_row(wd.l[2 * nb + 2], 0, d3, y2, net.lin_in[2]);
         matmul_t_stream(wst, L.ck_blin[2], net.lin_in[2], net.lin_out[2], 1, d3, 0, d2, 0, y2);
+        MDQ_TRACE();  // backward: lin3^T
         emit_row(wd.l[2 * nb + 1], 0, d2, y1, net.lin_in[1]);
         matmul_t_stream(wst, L.ck_blin[1], net.lin_in[1], net.lin_out[1], 1, d2, 0, d1, 0, y1);
+        MDQ_TRACE();  // backward: lin2^T
         emit_row(wd.l[2 * nb + 0], 0, d1, racc, net.lin_in[0]);
         matmul_t_stream(wst, L.ck_blin[0], net.lin_in[0], net.lin_out[0], 1, d1, 0, dr, 0, nullptr);
     }

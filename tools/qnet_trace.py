@@ -11,8 +11,8 @@ g = torch.Generator().manual_seed(0)
 mk = lambda: Data(x=torch.randn(180, 17, generator=g), edge_index=torch.randint(0, 180, (2, 372), generator=g))
 net = NodeRemovalNet(181, 128, 0.1); net.set_num_nodes(17); net = net.to(dev)
 FWD = ["start", "L1 load", "L1 csr", "L1 agg", "L1 dense", "L1 scores", "L1 rank", "L1 gather+readout+filter",
-       "B1 csr", "B1 conv", "B1 pool", "B2 csr", "B2 conv", "B2 pool", "B3 csr", "B3 conv", "B3 pool", "MLP", "softmax"]
-BWD = FWD + ["bwd MLP", "bwd B3 start", "bwd B2 start", "bwd B1 start", "bwd B0 start", "bwd done"]
+       "B1 csr", "B1 conv", "B1 pool", "B2 csr", "B2 conv", "B2 pool", "B3 csr", "B3 conv", "B3 pool", "lin1", "lin2", "lin3 (MLP done)", "softmax"]
+BWD = FWD + ["bwd huber", "bwd lin3T", "bwd lin2T", "bwd lin1T (MLP done)", "bwd B3 start", "bwd B2 start", "bwd B1 start", "bwd B0 start", "bwd done"]
 L = _lib.lib()
 net._ensure_packed(); net._net.x_stride = 17
 print('occupancy CTAs/SM fwd', L.mdq_qnet_occupancy(net._net, 180, 372, 0), 'bwd', L.mdq_qnet_occupancy(net._net, 180, 372, 1))
