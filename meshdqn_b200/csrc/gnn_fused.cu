@@ -727,9 +727,10 @@ __device__ void mlp_stream(const WStream &ws, int j0, int rows, int K, int O, co
         c_[it] = rem - r_[it] * O;
     }
     int k = 0;
-    for (int jc = j0; k < K; ++jc) {
+    const bool whole = ws.ns == 0 && (K % SL) == 0;   // direct mode: the weights are one contiguous [K][O] block, so the
+    for (int jc = j0; k < K; ++jc) {                  // k loop runs once over all of K (clean 16-deep load batches)
         const float *st = ws.wait(jc);
-        const int cr = ws.rows(jc);
+        const int cr = whole ? K : ws.rows(jc);
         const int per = cr / SL;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
@@ -758,11 +759,83 @@ __device__ void mlp_stream(const WStream &ws, int j0, int rows, int K, int O, co
     __syncthreads();
 }
 
+// out[r][k] = gate(k) * sum_c D[r][c] * WT[k][c] for one or two delta rows: a warp per weight row, lanes along c (NCI
+// 32-float pieces per row), RB rows in flight per warp, butterfly reduction per row.
+template <int NCI, int RB, bool TWO>
+__device__ __forceinline__ void matmul_t_rows(const float *__restrict__ WT, int K, int C, const float *D, int ldd, float *out,
+                                              int ldo, const float *gate)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float d0[NCI], d1[NCI];
+#pragma unroll
+    for (int i = 0; i < NCI; ++i) {
+        const int c = lane + 32 * i;
+        d0[i] = c < C ? D[c] : 0.f;
+        d1[i] = (TWO && c < C) ? D[ldd + c] : 0.f;
+    }
+    for (int kb = warp * RB; kb < K; kb += NWARP * RB) {
+        float w[RB][NCI];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const float *wrow = WT + (size_t)min(kb + j, K - 1) * C;
+#pragma unroll
+            for (int i = 0; i < NCI; ++i) {
+                const int c = lane + 32 * i;
+                w[j][i] = c < C ? __ldg(wrow + c) : 0.f;
+            }
+        }
+        float a0[RB], a1[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            a0[j] = 0.f;
+            a1[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NCI; ++i) {
+                a0[j] = fmaf(d0[i], w[j][i], a0[j]);
+                if (TWO) a1[j] = fmaf(d1[i], w[j][i], a1[j]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                a0[j] += __shfl_xor_sync(FULL, a0[j], o);
+                if (TWO) a1[j] += __shfl_xor_sync(FULL, a1[j], o);
+            }
+        }
+        float v0 = a0[0], v1 = a1[0];
+#pragma unroll
+        for (int j = 1; j < RB; ++j) {
+            if (lane == j) { v0 = a0[j]; v1 = a1[j]; }
+        }
+        if (lane < RB && kb + lane < K) {
+            const int k = kb + lane;
+            const bool on = (gate == nullptr || gate[k] > 0.f);
+            out[k] = on ? v0 : 0.f;
+            if (TWO) out[ldo + k] = on ? v1 : 0.f;
+        }
+    }
+}
+
 // out[r][k] = gate(k) * sum_c D[r][c] * WT[k][c]: input gradients; one warp per (r, k), lanes over c.
 __device__ void matmul_t_stream(const WStream &ws, int j0, int K, int C, int nr, const float *D, int ldd, float *out, int ldo,
                                 const float *gate)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ws.ns == 0 && nr <= 2 && C <= 256) {
+        // direct mode, MLP-sized (one or two delta rows): a warp per weight row k, lanes along c -- every load is a
+        // coalesced piece of the row (a thread per row touched 32 different lines per request and was bound by the L1
+        // tag rate; the generic path below issued its loads one dependent round trip at a time)
+        const float *WT = ws.params + ws.ck->off[j0];
+        const int nci = (C + 31) >> 5;
+        const bool two = nr == 2;
+        if (nci <= 2) { if (two) matmul_t_rows<2, 8, true>(WT, K, C, D, ldd, out, ldo, gate); else matmul_t_rows<2, 8, false>(WT, K, C, D, ldd, out, ldo, gate); }
+        else if (nci <= 4) { if (two) matmul_t_rows<4, 8, true>(WT, K, C, D, ldd, out, ldo, gate); else matmul_t_rows<4, 8, false>(WT, K, C, D, ldd, out, ldo, gate); }
+        else if (nci <= 6) { if (two) matmul_t_rows<6, 4, true>(WT, K, C, D, ldd, out, ldo, gate); else matmul_t_rows<6, 4, false>(WT, K, C, D, ldd, out, ldo, gate); }
+        else { if (two) matmul_t_rows<8, 4, true>(WT, K, C, D, ldd, out, ldo, gate); else matmul_t_rows<8, 4, false>(WT, K, C, D, ldd, out, ldo, gate); }
+        __syncthreads();
+        return;
+    }
     if (ws.ns == 0 && (C & 3) == 0) {
         // direct mode: one thread per weight row k (rows are contiguous in memory, 16-byte loads, many in flight),
         // delta rows broadcast from shared memory; two delta rows per pass
