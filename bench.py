@@ -178,6 +178,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for multi-process launches; the reference arm is rank 0 alone on the host's
+    # cores, so give it all of them back
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     tr = harvest_transitions(env_factory(None), BATCH, 1000)
     k, dt = cpu_replay_steps(tr, max_seconds=120.0, max_steps=args.steps, warmup=min(args.warmup, 2))
     val = BATCH * k / dt
