@@ -443,6 +443,20 @@ def measure_extras(dev, net, rb_dev, flush, args):
             fi()
         ms = time_events(fi, 20, flush)
     out["env_step_ys930"] = {"steps_per_s": n / dt, "ms_per_step": 1e3 * dt / n, "note": "Q-eval + Qhull (host) + device step"}
+    # replicas: the single-episode step does not shard, so rollout throughput comes from independent
+    # environments -- one host thread + one CUDA stream each on the same GPU (the reference uses 12 Ray workers)
+    from meshdqn_b200.parallel import run_env_replicas
+    with quiet():
+        rngs = {}
+
+        def pol(env, s, k):
+            r = rngs.setdefault(id(env), np.random.RandomState(len(rngs)))
+            return int(r.randint(0, 180))
+        run_env_replicas(mk, pol, 2, 3, dev)                       # warm-up (per-thread streams, allocator pools)
+        nrep = 16
+        tot, wall = run_env_replicas(mk, pol, nrep, 16, dev)
+    out["env_step_ys930_replicas"] = {"replicas": nrep, "steps_per_s": tot / wall, "steps": tot,
+                                      "note": "independent environments on one GPU, one host thread + CUDA stream each"}
     npt = m1.nv + m1.ne
     out["reinterp_ys930"] = {"vertices_per_s": npt / (ms * 1e-3), "us_per_launch": ms * 1e3, "target_points": npt, "T": 5}
     # large synthetic mesh: full-field re-interpolation onto a coarsened copy (throughput mode, no smoothing)

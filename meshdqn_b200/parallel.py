@@ -81,3 +81,59 @@ def evaluate_candidates(q_eval, candidates, rank: int, world: int, group=None):
         parts.append(out[r][: rhi - rlo])
     table = torch.cat(parts, dim=0)
     return table[:, 0].long(), table[:, 1]
+
+
+def run_env_replicas(make_env, policy, n_envs: int, n_steps: int, device=None):
+    """Independent environment replicas on ONE GPU (the single-episode step does not shard --
+    "replicas only"; the reference gets its rollout parallelism from 12 Ray worker processes,
+    airfoil_dqn.py:428-503).
+
+    One host thread and one CUDA stream per replica: a replica's device work (re-triangulated mesh topology, the
+    ordered smoothing sweep -- a single-CTA, latency-bound kernel -- re-interpolation, drag/lift, state build) runs
+    concurrently with the other replicas' kernels on other SMs and with their host-side Qhull calls (PyTorch
+    releases the GIL while a thread blocks on its stream).  ``make_env()`` builds an environment on ``device``;
+    ``policy(env, state, k)`` returns the action of step k.  Episodes restart on termination.  Returns
+    (total environment steps, wall seconds).
+    """
+    import threading
+    import time
+
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    envs = [make_env() for _ in range(n_envs)]
+    states = [e.get_state() for e in envs]
+    torch.cuda.synchronize(dev)
+    counts = [0] * n_envs
+    errors = []
+    start = threading.Barrier(n_envs + 1)
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream(dev)
+            with torch.cuda.device(dev), torch.cuda.stream(stream):
+                env, s = envs[i], states[i]
+                start.wait()
+                for k in range(n_steps):
+                    s, _, done, _ = env.step(policy(env, s, k))
+                    counts[i] += 1
+                    if done:
+                        env = make_env()
+                        s = env.get_state()
+                stream.synchronize()
+        except Exception as exc:  # surfaced by the caller
+            errors.append(exc)
+            try:
+                start.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n_envs)]
+    for t in threads:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for t in threads:
+        t.join()
+    dt = time.perf_counter() - t0
+    if errors:
+        raise errors[0]
+    return sum(counts), dt
