@@ -216,7 +216,8 @@ int mdq_grid_fill(const double *coords0, const int32_t *cells0, int nc0, const d
  *   target P2 dof points = vertices [nv] then edge midpoints 0.5*a+0.5*b [ne];
  *   located in M0: lowest-index cell with min barycentric >= -tol, else the closest cell (lowest index on ties);
  *   U0 [T][nv0+ne0][2], P0 [T][nv0]  ->  U [T][nv+ne][2], P [T][nv], cell_of [nv+ne] i32.
- *   miss_count: device int32 (points that needed the closest-cell fallback); miss_list [nv+ne] scratch. */
+ *   miss_count: device int32 (points that needed the closest-cell fallback); miss_list [nv+ne] scratch.
+ *   coords must be 16-byte aligned and edges 8-byte aligned (vector loads). */
 int mdq_interpolate(const double *coords, int nv, const int32_t *edges, int ne, const double *coords0,
                     const int32_t *cells0, const int32_t *cell_edges0, int nv0, int ne0, int nc0,
                     const double *h_grid, const int32_t *bin_ptr, const int32_t *bin_cells, double tol, int T,

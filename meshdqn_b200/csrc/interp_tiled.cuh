@@ -14,7 +14,7 @@
 //                     reject skips cells that cannot contain the point, and the exact test and the P2/P1
 //                     evaluation use the same operation sequence as the uniform-grid kernel and the oracle;
 //   k_tile_overflow : the (normally empty) overflow list, served straight from the leaf arrays in HBM; also
-//                     re-zeroes the counters for the next call;
+//                     re-zeroes the overflow counter for the next call (each per-leaf CTA re-zeroes its own);
 //   k_interp_miss   : closest-cell extrapolation for points outside every source cell (geom.cu).
 // HBM traffic is ~ the algorithmic bytes (every source byte is read once per leaf that overlaps it); all gathers
 // hit shared memory.
@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_interp(const TileArgs t)
     const double2 r1 = __ldg(reinterpret_cast<const double2 *>(t.leaf_rect + 4 * L) + 1);
     const int cnt = min(cnt_raw, b1 - b0);
     if (cnt == 0) return;
+    if (threadIdx.x == 0) t.leaf_cnt[L] = 0;   // only this CTA reads the counter: left zeroed for the next call
     const InterpArgs &a = t.a;
     const int T = a.T;
     const int vbase = i0.x, nvl = i0.y, dbase = i0.z, np2l = i0.w, cbase = i1.x, ncl = i1.y, bbase = i1.z, nbin = i1.w;
@@ -395,7 +396,6 @@ __global__ void __launch_bounds__(256) k_tile_overflow(const TileArgs t)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const int novf = __ldcg(t.ovf_count);
-    for (int l = gtid; l < t.n_leaves; l += gsz) t.leaf_cnt[l] = 0;
     const InterpArgs &a = t.a;
     const double margin = a.tol * (1.0 + 1e-6) + 1e-9;
     for (int m = gtid; m < novf; m += gsz) {
