@@ -1544,7 +1544,7 @@ __device__ __forceinline__ void wg_layer_geom(const WDesc &wd, int B, int li, in
     poff = off;
 }
 
-__global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int B, const float *__restrict__ ws,
+__global__ void __launch_bounds__(256, 3) wgrad_partial_kernel(const WDesc wd, int B, const float *__restrict__ ws,
                                                             float *__restrict__ partial)
 {
     __shared__ __align__(16) float xin[WG_ROWS][WG_KG];  // the chunk's input rows, these WG_KG k-values
@@ -1580,9 +1580,14 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const WDesc wd, int 
             for (int j = 0; j < WG_KG; ++j) acc[j] = 0.f;
             const float *dl = ws + l.d_off + c;
             const int nr = r1 - r0;
-#pragma unroll 8
-            for (int rr = 0; rr < nr; ++rr) {
-                const float d = __ldg(dl + (size_t)(r0 + rr) * l.C);
+            // all WG_ROWS delta loads of the chunk are issued together (one round trip instead of four); rows past the
+            // chunk's end contribute d = 0 against zero-filled inputs
+            float dv[WG_ROWS];
+#pragma unroll
+            for (int rr = 0; rr < WG_ROWS; ++rr) dv[rr] = rr < nr ? __ldg(dl + (size_t)(r0 + rr) * l.C) : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < WG_ROWS; ++rr) {
+                const float d = dv[rr];
                 const float4 xa = *reinterpret_cast<const float4 *>(&xin[rr][0]);
                 const float4 xb = *reinterpret_cast<const float4 *>(&xin[rr][4]);
                 acc[0] = fmaf(xa.x, d, acc[0]); acc[1] = fmaf(xa.y, d, acc[1]);
