@@ -98,18 +98,23 @@ def run_env_replicas(make_env, policy, n_envs: int, n_steps: int, device=None):
     import threading
     import time
 
+    import contextlib
+
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    on_gpu = dev.type == "cuda"          # a CPU device only exercises the host logic (tests); no streams there
     envs = [make_env() for _ in range(n_envs)]
     states = [e.get_state() for e in envs]
-    torch.cuda.synchronize(dev)
+    if on_gpu:
+        torch.cuda.synchronize(dev)
     counts = [0] * n_envs
     errors = []
     start = threading.Barrier(n_envs + 1)
 
     def worker(i):
         try:
-            stream = torch.cuda.Stream(dev)
-            with torch.cuda.device(dev), torch.cuda.stream(stream):
+            stream = torch.cuda.Stream(dev) if on_gpu else None
+            with (torch.cuda.device(dev) if on_gpu else contextlib.nullcontext()), \
+                    (torch.cuda.stream(stream) if on_gpu else contextlib.nullcontext()):
                 env, s = envs[i], states[i]
                 start.wait()
                 for k in range(n_steps):
@@ -118,7 +123,8 @@ def run_env_replicas(make_env, policy, n_envs: int, n_steps: int, device=None):
                     if done:
                         env = make_env()
                         s = env.get_state()
-                stream.synchronize()
+                if on_gpu:
+                    stream.synchronize()
         except Exception as exc:  # surfaced by the caller
             errors.append(exc)
             try:

@@ -153,3 +153,25 @@ def test_replay_batch_arena_packing_round_trip(monkeypatch):
             assert torch.equal(m[0], m0[0]) and torch.equal(m[1], m0[1]) and m[2:] == m0[2:]
             assert a.edge_index.data_ptr() % 16 == 0 and a.x.data_ptr() % 16 == 0
         assert rr.tensors()[0] is rr._arena and len(rr.tensors()) == 1
+
+
+def test_env_replicas_host_logic_on_cpu():
+    """run_env_replicas with the CPU oracle environment: every replica takes its steps, episodes restart on `done`."""
+    import io, contextlib
+    import torch
+    from conftest import make_config, oracle_fields
+    from meshdqn_b200.parallel import run_env_replicas
+    from oracle.env_ref import Env2DAirfoilRef
+    coords, cells, U, P = oracle_fields("ah93w145")
+    cfg = make_config()
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    made = []
+
+    def mk():
+        e = Env2DAirfoilRef(cfg, mesh=(coords, cells))
+        made.append(e)
+        return e
+    with contextlib.redirect_stdout(io.StringIO()):
+        tot, wall = run_env_replicas(mk, lambda env, s, k: (3 + 5 * k) % 180, 2, 2, torch.device("cpu"))
+    assert tot == 4 and wall > 0 and len(made) >= 2
+    assert all(e.steps >= 1 for e in made[:2])
