@@ -466,7 +466,7 @@ __device__ __forceinline__ unsigned desc_key(float s)
     return ~u;                                   // descending
 }
 
-constexpr int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+constexpr int RS_THREADS = 256, RS_ITEMS = 2, RS_TILE = RS_THREADS * RS_ITEMS;  // 512 keys per CTA: short per-warp chains (2 match_any steps), more CTAs in flight
 // table[digit][cta]
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const unsigned *__restrict__ key, int n, int shift,
                                                            int *__restrict__ table, int ncta)
@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const unsigned *__res
 
 // Stable scatter: warp w of the CTA owns the contiguous chunk [w*512, w*512+512) of the tile and walks it 32 keys at
 // a time; ranks inside a 32-key group come from match_any, offsets across groups / warps from counters.
+template <bool INLINE_SCAN>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned *__restrict__ key, const int *__restrict__ val,
                                                               int n, int shift, const int *__restrict__ table_ex, int ncta,
                                                               unsigned *__restrict__ key_out, int *__restrict__ val_out)
@@ -507,7 +508,32 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned *__
     // bases: global (table_ex[digit][cta]) + digits counted by lower warps of this CTA
     {
         const int d = threadIdx.x;  // 256 threads <-> 256 digits
-        int run = table_ex[d * ncta + blockIdx.x];
+        int run;
+        if (INLINE_SCAN) {
+            // table_ex holds the RAW counts table[digit][cta]: every CTA forms its own exclusive bases (digit-major
+            // prefix) from it -- ncta loads per thread and one block scan -- instead of a scan launch per pass
+            __shared__ int wsum[NW];
+            int tot = 0, before = 0;
+            for (int c = 0; c < ncta; ++c) {
+                const int v = table_ex[d * ncta + c];
+                before += (c < (int)blockIdx.x) ? v : 0;
+                tot += v;
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            int wbase2 = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) wbase2 += (w < warp) ? wsum[w] : 0;
+            run = wbase2 + incl - tot + before;
+        } else {
+            run = table_ex[d * ncta + blockIdx.x];
+        }
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int c = cnt[w][d];
@@ -555,13 +581,19 @@ __global__ void k_select_init(const float *__restrict__ score, int n, unsigned *
         hist[threadIdx.x & 255] = 0;
         if (threadIdx.x == 0) {
             st->prefix = 0u; st->mask = 0u; st->remaining = k; st->count_lt = 0;
+            reinterpret_cast<int *>(st)[4] = 0;   // ticket of k_select_hist's last-CTA pick
         }
     }
 }
-__global__ void __launch_bounds__(256) k_select_hist(const unsigned *__restrict__ key, int n, int shift,
-                                                     const SelState *__restrict__ st, int *__restrict__ hist)
+// One launch per 8-bit digit: every CTA histograms the keys still matching the prefix; the LAST CTA to finish (ticket)
+// picks the digit whose cumulative count first reaches `remaining`, extends the prefix and re-zeroes the histogram
+// (a separate single-CTA pick launch per pass cost as much as the histogram itself on the small levels).
+__global__ void __launch_bounds__(256) k_select_hist(const unsigned *__restrict__ key, int n, int shift, SelState *st,
+                                                     int *__restrict__ hist)
 {
     __shared__ int h[256];
+    __shared__ int wsum[8];
+    __shared__ int is_last;
     h[threadIdx.x] = 0;
     __syncthreads();
     const unsigned prefix = st->prefix, mask = st->mask;
@@ -571,12 +603,15 @@ __global__ void __launch_bounds__(256) k_select_hist(const unsigned *__restrict_
     }
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(hist + threadIdx.x, h[threadIdx.x]);
-}
-__global__ void __launch_bounds__(256) k_select_pick(SelState *st, int *__restrict__ hist, int shift)
-{
-    __shared__ int wsum[8];
+    __threadfence();
+    __syncthreads();
+    int *ticket = reinterpret_cast<int *>(st) + 4;
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = hist[threadIdx.x];
+    const int c = __ldcg(hist + threadIdx.x);
     hist[threadIdx.x] = 0;   // ready for the next pass
     int incl = c;
 #pragma unroll
@@ -595,11 +630,12 @@ __global__ void __launch_bounds__(256) k_select_pick(SelState *st, int *__restri
     const bool hit = (incl >= need && incl - c < need) || (threadIdx.x == 255 && incl < need);
     if (hit) {
         const int cum = incl - c;
-        st->prefix |= (unsigned)threadIdx.x << shift;
-        st->mask |= 255u << shift;
+        st->prefix = prefix | ((unsigned)threadIdx.x << shift);
+        st->mask = mask | (255u << shift);
         st->remaining = need - cum;
         st->count_lt += cum;
     }
+    if (threadIdx.x == 0) *ticket = 0;
 }
 constexpr int SC_TILE = 4096;
 __global__ void __launch_bounds__(1024) k_select_count(const unsigned *__restrict__ key, int n, const SelState *__restrict__ st,
@@ -961,8 +997,12 @@ int radix_sort_pairs(int n, unsigned *key_a, unsigned *key_b, int *val_a, int *v
     for (int shift = 0; shift < 32; shift += 8) {
         k_radix_hist<<<ncta, RS_THREADS, 0, st>>>(kin, n, shift, table, ncta);
         if ((rc = mdq::check_launch("k_radix_hist"))) return rc;
-        if ((rc = scan_i32(table, table + 256 * ncta + 8, 256 * ncta, scan_part, st))) return rc;
-        k_radix_scatter<<<ncta, RS_THREADS, 0, st>>>(kin, vin, n, shift, table + 256 * ncta + 8, ncta, kout, vout);
+        if (ncta <= 256) {   // every CTA scans the small count table itself: no scan launch
+            k_radix_scatter<true><<<ncta, RS_THREADS, 0, st>>>(kin, vin, n, shift, table, ncta, kout, vout);
+        } else {
+            if ((rc = scan_i32(table, table + 256 * ncta + 8, 256 * ncta, scan_part, st))) return rc;
+            k_radix_scatter<false><<<ncta, RS_THREADS, 0, st>>>(kin, vin, n, shift, table + 256 * ncta + 8, ncta, kout, vout);
+        }
         if ((rc = mdq::check_launch("k_radix_scatter"))) return rc;
         unsigned *tk = kin; kin = kout; kout = tk;
         int *tv = vin; vin = vout; vout = tv;
@@ -986,8 +1026,6 @@ int topk_select_sort(const float *score, int n, int k, unsigned *key_all, unsign
     for (int shift = 24; shift >= 0; shift -= 8) {
         k_select_hist<<<grid_for(n, 256 * 8, 148 * 4), 256, 0, st>>>(key_all, n, shift, state, hist);
         if ((rc = mdq::check_launch("k_select_hist"))) return rc;
-        k_select_pick<<<1, 256, 0, st>>>(state, hist, shift);
-        if ((rc = mdq::check_launch("k_select_pick"))) return rc;
     }
     k_select_count<<<nparts, 1024, 0, st>>>(key_all, n, state, part_lt, part_eq);
     if ((rc = mdq::check_launch("k_select_count"))) return rc;
