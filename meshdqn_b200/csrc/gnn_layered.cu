@@ -1013,10 +1013,48 @@ int radix_sort_pairs(int n, unsigned *key_a, unsigned *key_b, int *val_a, int *v
 
 // TopKPooling's perm: the k best rows by (score desc, index asc), in that order.
 //   key_all [n]; key_a/key_b/val_a/val_b [>= k]; sel: SelState + 256-int histogram + 4 * (cdiv(n, SC_TILE) + 2) ints
+// Small levels (n <= TS_MAX rows): ONE single-CTA launch instead of the ~17 of select + sort -- bitonic sort of the
+// 64-bit composites (descending-score key << 32 | row index) in shared memory, the first k of the ascending order are
+// the kept rows in exactly the order select + stable LSD sort produce (score descending, ties by lower index).
+constexpr int TS_MAX = 8192, TS_THREADS = 1024;
+__global__ void __launch_bounds__(TS_THREADS) k_topk_small(const float *__restrict__ score, int n, int k, int n2,
+                                                           int *__restrict__ perm)
+{
+    extern __shared__ unsigned long long ts_arr[];
+    for (int i = threadIdx.x; i < n2; i += TS_THREADS)
+        ts_arr[i] = i < n ? (((unsigned long long)desc_key(score[i]) << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += TS_THREADS) {
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));   // element whose `stride` bit is 0
+                const int hi = lo | stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = ts_arr[lo], b = ts_arr[hi];
+                if ((a > b) == up) { ts_arr[lo] = b; ts_arr[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = threadIdx.x; r < k; r += TS_THREADS) perm[r] = (int)(unsigned)(ts_arr[r] & 0xffffffffull);
+}
+
 int topk_select_sort(const float *score, int n, int k, unsigned *key_all, unsigned *key_a, unsigned *key_b, int *val_a,
                      int *val_b, int *table, int *scan_part, int *sel, int **perm, cudaStream_t st)
 {
     int rc;
+    if (n <= TS_MAX) {
+        int n2 = 2;
+        while (n2 < n) n2 <<= 1;
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_topk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_MAX * 8);
+            configured = true;
+        }
+        k_topk_small<<<1, TS_THREADS, (size_t)n2 * 8, st>>>(score, n, k, n2, val_a);
+        *perm = val_a;
+        return mdq::check_launch("k_topk_small");
+    }
     SelState *state = reinterpret_cast<SelState *>(sel);
     int *hist = sel + 8;
     const int nparts = cdiv(n, SC_TILE);
