@@ -289,6 +289,49 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     e2e_val = world * BATCH * K / e2e_s
 
+    # ---- the same loop fed from the DEVICE-resident replay memory -- sample (host-side index
+    # draw + ~12 KB of offsets over PCIe + one gather launch) + step + lagged loss read-back; no minibatch H2D ----
+    from meshdqn_b200.replay import DeviceReplayMemory
+    e_cap = max(max(int(t[0].edge_index.shape[1]), int(t[2].edge_index.shape[1]) if t[2] is not None else 0) for t in tr)
+    mem = DeviceReplayMemory(capacity=BATCH, n_max=180, e_max=e_cap, n_features=int(tr[0][0].x.shape[1]), device=dev)
+    for s_, a_, s2_, r_ in tr:
+        mem.push(s_, a_, s2_, r_)
+    mrng = np.random.RandomState(1234 + rank)
+
+    def mem_loop(n):
+        evs = []
+        for k in range(n):
+            loss = trainer.step(mem.sample(BATCH, rng=mrng))
+            loss_host[k:k + 1].copy_(loss, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            evs.append(ev)
+            if k >= 1:
+                evs[k - 1].synchronize()
+                float(loss_host[k - 1])
+        evs[-1].synchronize()
+    mem_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    mem_loop(K)
+    barrier()
+    mem_s = max_over_ranks(time.perf_counter() - t0, dev)
+    mem_val = world * BATCH * K / mem_s
+    # the loop the reference runs (airfoil_dqn.py:240-257): a NEW sample every step, collated on the host, copied over
+    hrng = np.random.RandomState(99 + rank)
+
+    def host_resample_loop(n):
+        for _ in range(n):
+            pick = hrng.choice(len(tr), BATCH, replace=False)
+            rb = ReplayBatch.from_transitions([tr[i] for i in pick]).pin_memory().to(dev)
+            float(trainer.step(rb))
+    host_resample_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    host_resample_loop(6)
+    barrier()
+    host_val = world * BATCH * 6 / max_over_ranks(time.perf_counter() - t0, dev)
+
     # ---- per-kernel durations (CUDA events around each launch group) for the roofline object ----
     trainer.timers = {}
     for _ in range(K):
@@ -333,6 +376,11 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": dom_us,
                              "note": "launch/latency-bound at 256 x 180-node graphs (15 KB per graph); see DESIGN.md"},
                 "kernel_us": kern, "extras": extras}
+        line["extras"]["replay_device_memory"] = {
+            "graphs_per_s": mem_val, "unit": UNIT, "host_resample_collate_graphs_per_s": host_val,
+            "note": "same step, minibatch sampled from the device-resident replay memory (one gather launch, ~12 KB of "
+                    "offsets over PCIe per step instead of the ~10 MB minibatch); host_resample_collate = a new sample collated on "
+                    "the host and copied every step, the loop the reference runs; SURVEY.md 8(f) row 1"}
         if world == 1 and not args.no_cpu:
             k, dt = cpu_replay_steps(tr, max_seconds=15.0, max_steps=1000, warmup=1)
             line["cpu_baseline"] = {"value": BATCH * k / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

@@ -282,6 +282,27 @@ int mdq_build_state(const double *dist, const int32_t *removable_idx, int nrem, 
                     const double *P, int32_t *n_closest, int32_t *coord_map, int32_t *inv_map, float *x,
                     int64_t *edge_index, int ecap, int32_t *n_edges, void *stream);
 
+/* ---- device-resident replay memory (replaces the host deque + DataLoader collation of airfoil_dqn.py:48-67,256,268) ----
+ * Slots: x_buf [cap][n_max][F] f32, ei_buf [cap][2][e_max] i32 (slot-local node ids), n_nodes / n_edges [cap] i32;
+ * one set for the states, one for the next states.
+ * mdq_replay_store: copy one graph (x [n][ldx], PyG int64 edge_index [2][E]) into `slot`.
+ * mdq_replay_gather: assemble the minibatch idx[0..B) as PyG-collated tensors in ONE launch:
+ *   x_out [ptr[B]][F], ei_out int64 [2][e_tot] (node offsets added), batch_out int64 [ptr[B]]; ptr / eptr i32 [B+1]
+ *   are the offsets of the collated batch (the host mirrors the slot sizes, so it provides them without a sync);
+ *   next states (xn_out != NULL): transition b's next state goes to row next_slot[b] (>= 0) of the second batch
+ *   with offsets nptr / neptr, terminal transitions (next_slot < 0) are skipped;
+ *   act_out / rew_out (nullable) [B] = act_buf / rew_buf [cap] gathered through idx. */
+int mdq_replay_store(const float *x, int ldx, int n, int F, const int64_t *edge_index, int E, float *x_buf,
+                     int32_t *ei_buf, int32_t *n_nodes, int32_t *n_edges, int64_t slot, int n_max, int e_max,
+                     void *stream);
+int mdq_replay_gather(const float *x_buf, const int32_t *ei_buf, const int32_t *n_nodes, const int32_t *n_edges,
+                      const float *xn_buf, const int32_t *ein_buf, const int32_t *nn_nodes, const int32_t *nn_edges,
+                      int n_max, int e_max, int F, const int64_t *idx, int B, const int32_t *ptr, const int32_t *eptr,
+                      int64_t e_tot, float *x_out, int64_t *ei_out, int64_t *batch_out, const int32_t *next_slot,
+                      const int32_t *nptr, const int32_t *neptr, int64_t ne_tot, float *xn_out, int64_t *ein_out,
+                      int64_t *nbatch_out, const int32_t *act_buf, const float *rew_buf, int32_t *act_out, float *rew_out,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ _SOURCES = (
     ("gnn_fused.cu", ()),
     ("gnn_layered.cu", ()),
     ("geom.cu", ("-fmad=false",)),
+    ("replay_buffer.cu", ()),
 )
 _NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "-I" + os.path.join(_ROOT, "include"), "-I" + _CSRC)
@@ -123,6 +124,9 @@ _SIGS = {
     "mdq_interpolate_tiled": (c_int, [_P, c_int, _P, c_int, POINTER(mdq_tile_index_t), _P, _P, _P, c_int, c_int, c_int,
                                       _P, _P, c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mdq_drag_lift": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_double, _P, _P]),
+    "mdq_replay_store": (c_int, [_P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "mdq_replay_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, c_int64, _P, _P, _P,
+                                  _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mdq_build_state": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P,
                                 _P, _P, c_int, _P, _P]),
 }

@@ -303,3 +303,188 @@ class ReplayTrainer:
         if self.num_grads % self.target_update == 0:
             self.select = not self.select
         return loss
+
+
+class DeviceReplayMemory:
+    """``ReplayMemory`` (/root/reference/airfoil_dqn.py:48-67: ``push(*Transition)``, ``sample(batch_size)``,
+    ``__len__``) with the transitions resident on the device and the minibatch collated by one gather launch.
+
+    The reference keeps a host ``deque`` of PyG ``Data`` objects and every training step runs
+    ``DataLoader(batch)`` collation on the host plus a host->device copy of the whole minibatch
+    (:240-257).  Here a transition is stored once, into fixed-size device slots (``mdq_replay_store``; the
+    states arrive from ``Env2DAirfoil.get_state`` already on the device), and ``sample`` assembles the
+    PyG-collated ``ReplayBatch`` with ``mdq_replay_gather``.  The host mirrors only the slots' sizes and
+    terminal flags, so it knows every offset / launch parameter of the minibatch without synchronising; what
+    crosses PCIe per step is one ~12 KB metadata block instead of the ~10 MB minibatch.
+
+    Ring buffer of ``capacity`` transitions (the oldest is overwritten, as ``deque(maxlen=capacity)`` does);
+    ``sample`` draws without replacement like ``random.sample`` (:63-64).  The collated tensors are
+    identical to ``ReplayBatch.from_transitions`` of the same transitions in the sampled order.
+    """
+
+    def __init__(self, capacity, n_max, e_max, n_features, device):
+        self.capacity, self.n_max, self.e_max, self.F = int(capacity), int(n_max), int(e_max), int(n_features)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceReplayMemory lives on a CUDA device (meshdqn_b200 has no CPU path)")
+        d = self.device
+        f32, i32 = dict(dtype=torch.float32, device=d), dict(dtype=torch.int32, device=d)
+        self.x = [torch.zeros((self.capacity, self.n_max, self.F), **f32) for _ in range(2)]      # state, next state
+        self.ei = [torch.zeros((self.capacity, 2, max(self.e_max, 1)), **i32) for _ in range(2)]
+        self.nn = [torch.zeros(self.capacity, **i32) for _ in range(2)]
+        self.ne = [torch.zeros(self.capacity, **i32) for _ in range(2)]
+        self.actions = torch.zeros(self.capacity, **i32)
+        self.rewards = torch.zeros(self.capacity, **f32)
+        import numpy as np
+        self._np = np
+        self.h_nn = np.zeros((2, self.capacity), dtype=np.int64)     # host mirrors: sizes and terminal flags
+        self.h_ne = np.zeros((2, self.capacity), dtype=np.int64)
+        self.h_has_next = np.zeros(self.capacity, dtype=bool)
+        self.size, self.head = 0, 0
+
+    def __len__(self):
+        return self.size
+
+    def _store(self, side, slot, data):
+        x = data.x
+        if x.device != self.device:
+            x = x.to(self.device, non_blocking=True)
+        x = x.float()
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        ei = data.edge_index
+        if ei.device != self.device:
+            ei = ei.to(self.device, non_blocking=True)
+        if ei.dtype != torch.int64 or not ei.is_contiguous():
+            ei = ei.to(torch.int64).contiguous()
+        n, E = int(x.shape[0]), int(ei.shape[1])
+        if x.shape[1] != self.F:
+            raise ValueError(f"state has {x.shape[1]} features, the memory was built for {self.F}")
+        if n > self.n_max or E > self.e_max:
+            raise ValueError(f"graph with {n} nodes / {E} edges exceeds the slot size ({self.n_max} / {self.e_max})")
+        L, p = _lib.lib(), _lib.ptr
+        with torch.cuda.device(self.device):
+            rc = L.mdq_replay_store(p(x), int(x.stride(0)), n, self.F, p(ei) if E else None, E, p(self.x[side]),
+                                    p(self.ei[side]), p(self.nn[side]), p(self.ne[side]), slot, self.n_max,
+                                    max(self.e_max, 1), _lib.stream_ptr())
+        _lib.check(rc, "mdq_replay_store")
+        self.h_nn[side, slot], self.h_ne[side, slot] = n, E
+
+    def push(self, state, action, next_state, reward):
+        """One ``Transition(state, action, next_state, reward)`` (airfoil_dqn.py:46-47,58-60); ``next_state`` None = terminal."""
+        slot = self.head
+        self._store(0, slot, state)
+        self.h_has_next[slot] = next_state is not None
+        if next_state is not None:
+            self._store(1, slot, next_state)
+        self.actions[slot] = int(action)
+        self.rewards[slot] = float(reward)
+        self.head = (self.head + 1) % self.capacity
+        self.size = min(self.size + 1, self.capacity)
+
+    # -- minibatch assembly ------------------------------------------------------------------------
+    _META_RING = 8          # pinned metadata blocks in flight (a block is reused after its copy's event completed)
+
+    def _meta_block(self, nbytes):
+        ring = self.__dict__.setdefault("_ring", [])
+        pos = self.__dict__.get("_ring_pos", 0)
+        if len(ring) < self._META_RING:
+            ring.append([torch.empty(max(nbytes, 4096), dtype=torch.uint8).pin_memory(), None])
+            slot = ring[-1]
+        else:
+            slot = ring[pos % self._META_RING]
+            if slot[1] is not None:
+                slot[1].synchronize()
+            if slot[0].numel() < nbytes:
+                slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.__dict__["_ring_pos"] = pos + 1
+        return slot
+
+    def sample(self, batch_size, rng=None, idx=None) -> "ReplayBatch":
+        """A collated minibatch on the device.  ``idx`` (host ints) fixes the transitions (tests); otherwise
+        ``rng`` (a ``numpy.random.RandomState`` / ``Generator``) or numpy's global generator draws them without
+        replacement.  Host work: the index draw, five cumulative sums over B integers and one pinned block of
+        int64 metadata -> one H2D copy -> one gather launch (which also gathers actions and rewards)."""
+        from .data import Batch
+        np = self._np
+        B = int(batch_size)
+        if idx is None:
+            if B > self.size:
+                raise ValueError(f"sample of {B} from a memory of {self.size}")
+            idx = (rng if rng is not None else np.random).choice(self.size, B, replace=False)
+        idx = np.asarray(idx, dtype=np.int64)
+        B = len(idx)
+        has_next = self.h_has_next[idx]
+        n_next = int(has_next.sum())
+        G2 = max(n_next, 1)
+        # metadata block, all int64 words then the int32 arrays: [idx B | ptr B+1 | eptr B+1 | nptr G2+1 | neptr G2+1]
+        # then int32 [ptr | eptr | nptr | neptr | next_slot B | owner G2]
+        n64 = B + 2 * (B + 1) + 2 * (G2 + 1)
+        n32 = 2 * (B + 1) + 2 * (G2 + 1) + B + G2
+        nbytes = 8 * n64 + 4 * n32
+        slot = self._meta_block(nbytes)
+        hb = slot[0].numpy()
+        w64 = hb[:8 * n64].view(np.int64)
+        w32 = hb[8 * n64:8 * n64 + 4 * n32].view(np.int32)
+        o = [0, B, 2 * B + 1, 3 * B + 2, 3 * B + 2 + G2 + 1, n64]
+        w64[:B] = idx
+        ptr, eptr, nptr, neptr = (w64[o[i]:o[i + 1]] for i in range(1, 5))
+        ptr[0] = eptr[0] = nptr[0] = neptr[0] = 0
+        np.cumsum(self.h_nn[0, idx], out=ptr[1:])
+        np.cumsum(self.h_ne[0, idx], out=eptr[1:])
+        nidx = idx[has_next]
+        nptr[1:] = 0
+        neptr[1:] = 0
+        if n_next:
+            np.cumsum(self.h_nn[1, nidx], out=nptr[1:])
+            np.cumsum(self.h_ne[1, nidx], out=neptr[1:])
+        p = [0, B + 1, 2 * B + 2, 2 * B + 2 + G2 + 1, 2 * B + 2 + 2 * (G2 + 1), 2 * B + 2 + 2 * (G2 + 1) + B, n32]
+        w32[p[0]:p[1]] = ptr
+        w32[p[1]:p[2]] = eptr
+        w32[p[2]:p[3]] = nptr
+        w32[p[3]:p[4]] = neptr
+        w32[p[4]:p[5]] = np.where(has_next, np.cumsum(has_next) - 1, -1)
+        w32[p[5]:p[6]] = np.nonzero(has_next)[0] if n_next else 0
+        N, E, Nn, En = int(ptr[-1]), int(eptr[-1]), int(nptr[-1]), int(neptr[-1])
+        mx = (int(np.diff(ptr).max()), int(np.diff(eptr).max()),
+              int(np.diff(nptr).max()) if n_next else 0, int(np.diff(neptr).max()) if n_next else 0)
+        d = self.device
+        meta = torch.empty(nbytes, dtype=torch.uint8, device=d)
+        meta.copy_(slot[0][:nbytes], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+        m64 = meta[:8 * n64].view(torch.int64)
+        m32 = meta[8 * n64:].view(torch.int32)
+        v64 = [m64[o[i]:o[i + 1]] for i in range(5)]
+        v32 = [m32[p[i]:p[i + 1]] for i in range(6)]
+        x = torch.empty((N, self.F), dtype=torch.float32, device=d)
+        ei = torch.empty((2, E), dtype=torch.int64, device=d)
+        bvec = torch.empty(N, dtype=torch.int64, device=d)
+        act = torch.empty(B, dtype=torch.int32, device=d)
+        rew = torch.empty(B, dtype=torch.float32, device=d)
+        with_next = n_next > 0
+        xn = torch.empty((Nn, self.F), dtype=torch.float32, device=d) if with_next else None
+        ein = torch.empty((2, En), dtype=torch.int64, device=d) if with_next else None
+        bn = torch.empty(Nn, dtype=torch.int64, device=d) if with_next else None
+        L, q = _lib.lib(), _lib.ptr
+        with torch.cuda.device(d):
+            rc = L.mdq_replay_gather(q(self.x[0]), q(self.ei[0]), q(self.nn[0]), q(self.ne[0]), q(self.x[1]), q(self.ei[1]),
+                                     q(self.nn[1]), q(self.ne[1]), self.n_max, max(self.e_max, 1), self.F, q(v64[0]), B,
+                                     q(v32[0]), q(v32[1]), E, q(x), q(ei), q(bvec), q(v32[4]), q(v32[2]), q(v32[3]), En,
+                                     q(xn), q(ein), q(bn), q(self.actions), q(self.rewards), q(act), q(rew),
+                                     _lib.stream_ptr())
+        _lib.check(rc, "mdq_replay_gather")
+
+        def mk(xx, ee, bb, p64, e64, p32, e32, G, mn, me):
+            b = Batch(x=xx, edge_index=ee)
+            b.batch, b.ptr, b.eptr, b.num_graphs = bb, p64, e64, G
+            b.__dict__["_mdq_ptrs"] = (p32, e32, G, mn, me)
+            b.__dict__["_meta"] = b.__dict__["_mdq_ptrs"]
+            return b
+        states = mk(x, ei, bvec, v64[1], v64[2], v32[0], v32[1], B, mx[0], mx[1])
+        nexts = mk(xn, ein, bn, v64[3][:n_next + 1], v64[4][:n_next + 1], v32[2][:n_next + 1], v32[3][:n_next + 1],
+                   n_next, mx[2], mx[3]) if with_next else None
+        out = ReplayBatch(states, act, nexts, v32[4], rew, v32[5])
+        out._keep = meta                  # the metadata block backs the offset views
+        return out

@@ -175,3 +175,11 @@ def test_env_replicas_host_logic_on_cpu():
         tot, wall = run_env_replicas(mk, lambda env, s, k: (3 + 5 * k) % 180, 2, 2, torch.device("cpu"))
     assert tot == 4 and wall > 0 and len(made) >= 2
     assert all(e.steps >= 1 for e in made[:2])
+
+
+def test_device_replay_memory_has_no_cpu_path():
+    import pytest
+    import torch
+    from meshdqn_b200.replay import DeviceReplayMemory
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DeviceReplayMemory(16, 180, 400, 17, torch.device("cpu"))

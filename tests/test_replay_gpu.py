@@ -141,3 +141,51 @@ def test_huber_kernel_matches_torch(cuda_device):
         assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
         gref = a1.grad if select else a2.grad
         assert (gq.cpu() - gref).abs().max() < 1e-6
+
+
+def test_device_replay_memory_matches_host_collation(cuda_device):
+    """DeviceReplayMemory.sample (one gather launch) must return exactly what ReplayBatch.from_transitions builds on the
+    host for the same transitions in the same order -- features, PyG-offset edges, batch vector, offsets, actions,
+    rewards, next-state slots -- and train to the same loss; the ring overwrites the oldest transition."""
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    from meshdqn_b200.replay import DeviceReplayMemory, ReplayBatch, ReplayTrainer
+    g = torch.Generator().manual_seed(11)
+
+    def mk():
+        n = int(torch.randint(150, 181, (1,), generator=g))
+        e = int(torch.randint(300, 400, (1,), generator=g))
+        return Data(x=torch.randn(n, 17, generator=g), edge_index=torch.randint(0, n, (2, e), generator=g))
+    trs = [(mk(), int(torch.randint(0, 181, (1,), generator=g)), None if i % 7 == 3 else mk(), float(torch.rand(1, generator=g)))
+           for i in range(40)]
+    mem = DeviceReplayMemory(capacity=32, n_max=180, e_max=400, n_features=17, device=cuda_device)
+    for s, a, s2, r in trs:
+        mem.push(s.to(cuda_device), a, None if s2 is None else s2.to(cuda_device), r)
+    assert len(mem) == 32
+    live = trs[8:]                                   # slots 0..7 were overwritten by transitions 32..39
+    slot_tr = {(8 + i) % 32: live[i] for i in range(32)}
+    idx = [5, 31, 0, 12, 19, 7, 8, 30, 3, 11, 26]     # includes terminal transitions (i % 7 == 3)
+    got = mem.sample(len(idx), idx=idx)
+    ref = ReplayBatch.from_transitions([slot_tr[i] for i in idx]).to(cuda_device)
+    for name in ("states", "next_states"):
+        a, b = getattr(got, name), getattr(ref, name)
+        assert torch.equal(a.x, b.x) and torch.equal(a.edge_index, b.edge_index) and torch.equal(a.batch, b.batch)
+        assert torch.equal(a.ptr.cpu(), b.ptr.cpu()) and torch.equal(a.eptr.cpu(), b.eptr.cpu()) and a.num_graphs == b.num_graphs
+        pa, pb = a._mdq_ptrs, b._mdq_ptrs
+        assert torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1]) and pa[2:] == pb[2:]
+    assert torch.equal(got.actions, ref.actions) and torch.equal(got.rewards, ref.rewards)
+    assert torch.equal(got.next_slot, ref.next_slot) and torch.equal(got.owner, ref.owner)
+    losses = []
+    for batch in (got, ref):
+        torch.manual_seed(1370)
+        nets = []
+        for _ in range(2):
+            n = NodeRemovalNet(181, 128, 0.1)
+            n.set_num_nodes(17)
+            nets.append(n.to(cuda_device))
+        tr = ReplayTrainer(nets[0], nets[1], lr=1e-5, weight_decay=1e-6, gamma=1.0)
+        losses.append([float(tr.step(batch)) for _ in range(2)])
+    assert losses[0] == losses[1]
+    drawn = mem.sample(16, rng=np.random.RandomState(0))
+    assert drawn.states.num_graphs == 16 and int(drawn.states.ptr[-1]) == drawn.states.x.shape[0]
+    with pytest.raises(ValueError):
+        mem.push(Data(x=torch.randn(181, 17), edge_index=torch.zeros((2, 0), dtype=torch.long)).to(cuda_device), 0, None, 0.0)
