@@ -183,3 +183,40 @@ def test_device_replay_memory_has_no_cpu_path():
     from meshdqn_b200.replay import DeviceReplayMemory
     with pytest.raises(RuntimeError, match="CUDA"):
         DeviceReplayMemory(16, 180, 400, 17, torch.device("cpu"))
+
+
+def test_dqn_driver_host_pieces(tmp_path):
+    """epsilon schedule (airfoil_dqn.py:454), the DataHandler's five .npy files (:128-133) and the policy-net
+    checkpoint names / PyG state_dict keys (:214-218) -- the artefacts deploy_dqn.py and training_results/ read."""
+    import math
+    import torch
+    from meshdqn_b200 import dqn
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    assert dqn.epsilon_threshold(0) == 1.0
+    assert abs(dqn.epsilon_threshold(10000) - (0.01 + 0.99 * math.exp(-1.0))) < 1e-15
+    pre = str(tmp_path / "run" / "ys930_")
+    h = dqn.DataHandler(pre)
+    h.add_eps(1.0); h.add_eps(0.99); h.add_loss(0.5)
+    h.add_episode([0.1, -1.0], [3, 180])
+    h.add_episode([0.2], [7])
+    h.write()
+    assert np.allclose(np.load(pre + "reward.npy"), [-0.9, 0.2]) and len(np.load(pre + "eps.npy")) == 2
+    assert list(np.load(pre + "actions.npy", allow_pickle=True)[0]) == [3, 180]
+    assert len(np.load(pre + "rewards.npy", allow_pickle=True)) == 2 and np.load(pre + "losses.npy")[0] == 0.5
+    h2 = dqn.DataHandler(pre, restart=True)
+    assert h2.num_eps() == 2 and h2.save_dir.endswith("RESTART_")
+    torch.manual_seed(0)
+    nets = []
+    for _ in range(2):
+        n = NodeRemovalNet(181, conv_width=128, topk=0.1)
+        n.set_num_nodes(17)
+        nets.append(n)
+    dqn.save_policy_nets(pre, nets[0], nets[1])
+    sd = torch.load(pre + "policy_net_1.pt")
+    assert {"conv1.lin_l.weight", "conv1.lin_l.bias", "conv1.lin_r.weight", "conv4.lin.weight", "conv4.bias",
+            "pool1.weight", "lin3.weight", "lin3.bias"} <= set(sd)
+    assert tuple(sd["conv1.lin_l.weight"].shape) == (128, 17) and tuple(sd["lin3.weight"].shape) == (181, 64)
+    fresh = NodeRemovalNet(181, conv_width=128, topk=0.1)
+    fresh.set_num_nodes(17)
+    dqn.load_policy_nets(pre, fresh, fresh)
+    assert all(torch.equal(fresh.state_dict()[k], nets[1].state_dict()[k]) for k in sd)
