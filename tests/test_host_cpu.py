@@ -220,3 +220,28 @@ def test_dqn_driver_host_pieces(tmp_path):
     fresh.set_num_nodes(17)
     dqn.load_policy_nets(pre, fresh, fresh)
     assert all(torch.equal(fresh.state_dict()[k], nets[1].state_dict()[k]) for k in sd)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) must print ONE JSON line with the
+    contract's keys; ranks other than 0 print nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "replay_train_graphs_per_s" and d["unit"] == "graphs/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
