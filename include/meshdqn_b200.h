@@ -14,7 +14,9 @@
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no internal
  *     synchronisation, re-entrant per stream;
  *   - return 0 on success, a negative MDQ_E* code on failure (never throws);
- *     mdq_last_error() gives a thread-local message.
+ *     mdq_last_error() gives a thread-local message;
+ *   - one CUDA device per process (the deployment model: one process per GPU): the kernels' opt-in shared-memory
+ *     attributes are set once per process; several host threads may call concurrently on their own streams.
  */
 #ifndef MESHDQN_B200_H
 #define MESHDQN_B200_H
