@@ -341,6 +341,7 @@ class DeviceReplayMemory:
         self.h_ne = np.zeros((2, self.capacity), dtype=np.int64)
         self.h_has_next = np.zeros(self.capacity, dtype=bool)
         self.size, self.head = 0, 0
+        self._ring, self._ring_pos = [], 0
 
     def __len__(self):
         return self.size
@@ -386,18 +387,18 @@ class DeviceReplayMemory:
     _META_RING = 8          # pinned metadata blocks in flight (a block is reused after its copy's event completed)
 
     def _meta_block(self, nbytes):
-        ring = self.__dict__.setdefault("_ring", [])
-        pos = self.__dict__.get("_ring_pos", 0)
-        if len(ring) < self._META_RING:
-            ring.append([torch.empty(max(nbytes, 4096), dtype=torch.uint8).pin_memory(), None])
-            slot = ring[-1]
+        """[pinned uint8 buffer, event of its last H2D copy] -- a small ring, so a block is only rewritten after the
+        copy that read it has completed."""
+        if len(self._ring) < self._META_RING:
+            self._ring.append([torch.empty(max(nbytes, 4096), dtype=torch.uint8).pin_memory(), None])
+            slot = self._ring[-1]
         else:
-            slot = ring[pos % self._META_RING]
+            slot = self._ring[self._ring_pos % self._META_RING]
             if slot[1] is not None:
                 slot[1].synchronize()
             if slot[0].numel() < nbytes:
                 slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-        self.__dict__["_ring_pos"] = pos + 1
+        self._ring_pos += 1
         return slot
 
     def sample(self, batch_size, rng=None, idx=None) -> "ReplayBatch":
