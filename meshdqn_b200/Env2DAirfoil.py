@@ -209,6 +209,11 @@ class Env2DAirfoil:
         self.gt_time = np.atleast_1d(np.array(ap.get("gt_time", -1)))
 
         u, p = ap.get("u", -1), ap.get("p", -1)
+        if isinstance(u, str) and isinstance(p, str):
+            # the "load saved values" branch (Env2DAirfoil.py:126-133): snapshots written by set_plot_dir
+            # (<plot_dir>/snapshots/save_velocities.npy [T, V0+E0, 2], save_pressures.npy [T, V0]; this package's P2
+            # layout -- vertex dofs, then edge-midpoint dofs in lexicographic edge order -- not DOLFIN's dof numbering)
+            u, p = np.load(u), np.load(p)
         if isinstance(u, int) and u == -1:
             if "synthetic_fields" in ap:
                 from .synthetic import synthetic_fields

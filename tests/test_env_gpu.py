@@ -229,3 +229,25 @@ def test_tiled_interpolation_bit_identical_to_grid_path_and_oracle(cuda_device, 
     Ut, Pt, ct, mt = tiled.interpolate(far)
     assert torch.equal(ct, cg) and int(mt) == int(mg) and int(mt) >= 3
     assert torch.equal(Ut, Ug) and torch.equal(Pt, Pg)
+
+
+def test_snapshot_files_round_trip(cuda_device, tmp_path):
+    """set_plot_dir writes the reference's four snapshot files (Env2DAirfoil.py:432-449); an environment built from
+    the saved P2/P1 arrays (the ':126-133' load branch) reproduces the fields, the ground-truth drag and the state."""
+    from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
+    coords, cells, U, P = oracle_fields("ah93w145")
+    cfg = make_config()
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    env = Env2DAirfoil(cfg, mesh=(coords, cells), device=cuda_device)
+    d = str(tmp_path / "plots")
+    env.set_plot_dir(d)
+    v, pr = np.load(d + "/snapshots/velocities.npy"), np.load(d + "/snapshots/pressures.npy")
+    assert v.shape == (U.shape[0], len(coords), 2) and pr.shape == (U.shape[0], len(coords), 1)
+    assert np.array_equal(v, env.velocities) and np.array_equal(pr, env.pressures)
+    cfg2 = make_config()
+    cfg2["agent_params"]["u"] = d + "/snapshots/save_velocities.npy"
+    cfg2["agent_params"]["p"] = d + "/snapshots/save_pressures.npy"
+    env2 = Env2DAirfoil(cfg2, mesh=(coords, cells), device=cuda_device)
+    assert torch.equal(env2.U, env.U) and torch.equal(env2.P, env.P) and np.array_equal(env2.gt_drag, env.gt_drag)
+    s1, s2 = env.get_state(), env2.get_state()
+    assert torch.equal(s1.x, s2.x) and torch.equal(s1.edge_index, s2.edge_index)
