@@ -82,7 +82,7 @@ def pick_smem(leaf_bytes, mean_points, fit_fraction=0.98):
     return None
 
 
-def tri_rect_overlap(tri, rlo, rhi, eps, chunk=1 << 21):
+def tri_rect_overlap(tri, rlo, rhi, eps, chunk=1 << 20):
     """Conservative triangle / axis-aligned rectangle overlap (separating axes: x, y and the three edge normals).
 
     tri [n,3,2], rlo / rhi [n,2].  False only when some axis separates the two by more than `eps`, so every cell that
@@ -91,20 +91,26 @@ def tri_rect_overlap(tri, rlo, rhi, eps, chunk=1 << 21):
     n = len(tri)
     out = np.empty(n, dtype=bool)
     for s0 in range(0, n, chunk):
-        t, lo, hi = tri[s0:s0 + chunk], rlo[s0:s0 + chunk], rhi[s0:s0 + chunk]
-        keep = (t[:, :, 0].min(1) <= hi[:, 0] + eps) & (t[:, :, 0].max(1) >= lo[:, 0] - eps) & \
-               (t[:, :, 1].min(1) <= hi[:, 1] + eps) & (t[:, :, 1].max(1) >= lo[:, 1] - eps)
-        c = 0.5 * (lo + hi)
-        h = 0.5 * (hi - lo)
+        t = tri[s0:s0 + chunk]
+        px = [np.ascontiguousarray(t[:, i, 0]) for i in range(3)]      # component arrays: elementwise min / max of three
+        py = [np.ascontiguousarray(t[:, i, 1]) for i in range(3)]      # columns is much cheaper than ufunc.reduce over axis 1
+        lox, loy = rlo[s0:s0 + chunk, 0], rlo[s0:s0 + chunk, 1]
+        hix, hiy = rhi[s0:s0 + chunk, 0], rhi[s0:s0 + chunk, 1]
+        keep = (np.minimum(np.minimum(px[0], px[1]), px[2]) <= hix + eps) & \
+               (np.maximum(np.maximum(px[0], px[1]), px[2]) >= lox - eps) & \
+               (np.minimum(np.minimum(py[0], py[1]), py[2]) <= hiy + eps) & \
+               (np.maximum(np.maximum(py[0], py[1]), py[2]) >= loy - eps)
+        cx, cy = 0.5 * (lox + hix), 0.5 * (loy + hiy)
+        hx, hy = 0.5 * (hix - lox), 0.5 * (hiy - loy)
         for i in range(3):
-            a, b, o = t[:, i], t[:, (i + 1) % 3], t[:, (i + 2) % 3]
-            nx, ny = -(b[:, 1] - a[:, 1]), b[:, 0] - a[:, 0]
+            j, k = (i + 1) % 3, (i + 2) % 3
+            nx, ny = -(py[j] - py[i]), px[j] - px[i]
             nn = np.sqrt(nx * nx + ny * ny)
-            pa = nx * a[:, 0] + ny * a[:, 1]                      # = projection of b as well
-            po = nx * o[:, 0] + ny * o[:, 1]
+            pa = nx * px[i] + ny * py[i]                          # = projection of vertex j as well
+            po = nx * px[k] + ny * py[k]
             tmin, tmax = np.minimum(pa, po), np.maximum(pa, po)
-            pc = nx * c[:, 0] + ny * c[:, 1]
-            r = np.abs(nx) * h[:, 0] + np.abs(ny) * h[:, 1]
+            pc = nx * cx + ny * cy
+            r = np.abs(nx) * hx + np.abs(ny) * hy
             tol = eps * nn + 1e-14 * (np.abs(pc) + r + np.abs(tmin) + np.abs(tmax))   # eps in length units + rounding slack
             keep &= (pc - r <= tmax + tol) & (pc + r >= tmin - tol)
         out[s0:s0 + chunk] = keep
@@ -228,11 +234,16 @@ def build_tile_index(coords, cells, cell_edges, ne, U0, P0, leaf_cells=256, eps=
     eleaf_ = pl[rep]
     # candidate lists by triangle / bin-rectangle overlap, not bounding boxes: about half the entries, so a query walks
     # about half as many candidates before it reaches its cell
-    dxb, dyb = (w[:, 0] / gx)[eleaf_], (w[:, 1] / gy)[eleaf_]
-    blo = np.stack([x0[eleaf_] + bxi * dxb, y0[eleaf_] + byi * dyb], 1)
-    bhi = np.stack([x0[eleaf_] + (bxi + 1) * dxb, y0[eleaf_] + (byi + 1) * dyb], 1)
-    keep = tri_rect_overlap(xy[pc[rep]], blo, bhi, eps)
-    del blo, bhi
+    dxl, dyl = w[:, 0] / gx, w[:, 1] / gy
+    keep = np.empty(len(rep), dtype=bool)
+    CH = 1 << 20                                            # chunked: the gathered triangles are 48 bytes per pair
+    for s0 in range(0, len(rep), CH):
+        sl = slice(s0, s0 + CH)
+        lf = eleaf_[sl]
+        dxb, dyb = dxl[lf], dyl[lf]
+        blo = np.stack([x0[lf] + bxi[sl] * dxb, y0[lf] + byi[sl] * dyb], 1)
+        bhi = np.stack([x0[lf] + (bxi[sl] + 1) * dxb, y0[lf] + (byi[sl] + 1) * dyb], 1)
+        keep[sl] = tri_rect_overlap(xy[pc[rep[sl]]], blo, bhi, eps)
     rep, ebin, eleaf_ = rep[keep], ebin[keep], eleaf_[keep]
     elocal = rep - cptr[eleaf_]
     nbin = gx * gy
