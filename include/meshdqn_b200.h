@@ -226,6 +226,14 @@ int mdq_interpolate(const double *coords, int nv, const int32_t *edges, int ne, 
                     const double *U0, const double *P0, double *U, double *P, int32_t *cell_of,
                     int32_t *miss_count, int32_t *miss_list, void *stream);
 
+/* Strict mode of the interpolation pin (the reference's "INTERPOLATION BROKE" branch,
+ * Env2DAirfoil.py:569-573): after mdq_interpolate / mdq_interpolate_tiled, max_d2 (device f64) = the largest squared
+ * distance between a target point that fell outside every source cell and the closest cell it was given
+ * (0 when nothing missed).  The host compares it with a macroscopic threshold and returns code 2 above it. */
+int mdq_interp_miss_distance(const double *coords, int nv, const int32_t *edges, int ne, const double *coords0,
+                             const int32_t *cells0, const int32_t *cell_of, const int32_t *miss_count,
+                             const int32_t *miss_list, double *max_d2, void *stream);
+
 /* Tiled re-interpolation for large source meshes (same results as mdq_interpolate, bit for bit).
  * The index over M0 is built once on the host (meshdqn_b200/tile_index.py): k-d leaves of ~256 cells whose whole
  * working set (local coordinates, all T snapshots' P2/P1 coefficients, cell->dof table, micro-grid) is contiguous,

@@ -172,6 +172,7 @@ class SourceField:
             if rc != 0:
                 self._tile_counters.zero_()
             _lib.check(rc, "mdq_interpolate_tiled")
+            self.last_miss_list = miss_list
             return U, P, cell_of, miss
         with torch.cuda.device(d):
             rc = L.mdq_interpolate(p(target.coords), target.nv, p(target.edges), target.ne, p(m0.coords), p(m0.cells),
@@ -179,7 +180,21 @@ class SourceField:
                                    float(tol), self.T, p(self.U0), p(self.P0), p(U), p(P), p(cell_of), p(miss),
                                    p(miss_list), _lib.stream_ptr())
         _lib.check(rc, "mdq_interpolate")
+        self.last_miss_list = miss_list
         return U, P, cell_of, miss
+
+    def miss_distance(self, target: DeviceMesh, cell_of, miss):
+        """Largest distance between a target dof point that fell outside every source cell and the closest cell
+        it was evaluated in (strict mode of SURVEY.md A.7); one device scalar read-back."""
+        m0, d = self.mesh, self.mesh.device
+        out = torch.zeros(1, dtype=torch.float64, device=d)
+        L, p = _lib.lib(), _lib.ptr
+        with torch.cuda.device(d):
+            rc = L.mdq_interp_miss_distance(p(target.coords), target.nv, p(target.edges), target.ne, p(m0.coords),
+                                            p(m0.cells), p(cell_of), p(miss), p(self.last_miss_list), p(out),
+                                            _lib.stream_ptr())
+        _lib.check(rc, "mdq_interp_miss_distance")
+        return math.sqrt(float(out.item()))
 
 
 class Env2DAirfoil:
@@ -207,6 +222,11 @@ class Env2DAirfoil:
         self.goal_vertices = ap["goal_vertices"]
         self.plot_dir = ap.get("plot_dir", "")
         self.gt_time = np.atleast_1d(np.array(ap.get("gt_time", -1)))
+        # strict interpolation (optional): a target dof point farther than this from every source cell
+        # (a new edge cutting through the airfoil hole) makes the removal fail with code 2 like the reference's
+        # "INTERPOLATION BROKE" (Env2DAirfoil.py:569-573).  None (default): closest-cell extrapolation always.
+        st = ap.get("interp_strict_tol", None)
+        self.interp_strict_tol = None if st is None else float(st)
 
         u, p = ap.get("u", -1), ap.get("p", -1)
         if isinstance(u, str) and isinstance(p, str):
@@ -435,8 +455,21 @@ class Env2DAirfoil:
     def _check_mesh(self, mesh, selected_coord):
         if selected_coord in self.removable:
             fs = self.flow_solver
-            fs.remesh(mesh)                                          # smooth(50), tags, removable on device
-            U, P, cell_of, miss = self.source.interpolate(fs.mesh)   # all T snapshots from the ORIGINAL mesh (B6)
+            old = (fs.mesh, fs.tags, fs.removable_dev, fs.num_vertices, fs._removable_host)
+            try:
+                fs.remesh(mesh)                                          # smooth(50), tags, removable on device
+                U, P, cell_of, miss = self.source.interpolate(fs.mesh)   # all T snapshots from the ORIGINAL mesh (B6)
+                if self.interp_strict_tol is not None and \
+                        self.source.miss_distance(fs.mesh, cell_of, miss) > self.interp_strict_tol:
+                    raise RuntimeError("target dof point outside the source mesh by more than interp_strict_tol")
+            except RuntimeError as err:
+                # Env2DAirfoil.py:569-573: restore the old mesh, put the vertex back, report a broken removal.  (The
+                # reference restores only flow_solver.mesh; here the tags / removable mask go back with it so the
+                # environment stays consistent.)
+                print("INTERPOLATION BROKE", err)
+                fs.mesh, fs.tags, fs.removable_dev, fs.num_vertices, fs._removable_host = old
+                self.coordinate_list.insert(selected_coord, selected_coord)
+                return 2
             self.U, self.P = U, P
             self._velocities = None
             self._pressures = None

@@ -229,6 +229,8 @@ class _FusedQNet(nn.Module):
         self._net = net
         self._packed_ptr = flat.data_ptr()
         self._ws = None
+        self._wsplit = None          # derived weight copies are rebuilt from the new flat buffer
+        self._wgen = getattr(self, "_wgen", 0) + 1
 
     def _ensure_packed(self):
         flat = getattr(self, "_flat", None)
@@ -245,6 +247,16 @@ class _FusedQNet(nn.Module):
 
     def _named_flat_params(self):
         return self._entries
+
+    def _weights_version(self):
+        """Changes whenever the flat buffer may hold different numbers: in-place torch writes bump the parameters'
+        own version counters (``load_state_dict``, ``set_weights``, torch optimizers -- the flat tensor's counter does
+        NOT move, the parameters are separate views), raw-pointer writers (``mdq_adam_step``) call
+        ``_bump_weights()``, a re-pack allocates a new buffer."""
+        return (self._flat.data_ptr(), self._wgen, sum(p._version for _, p in self._entries))
+
+    def _bump_weights(self):
+        self._wgen = getattr(self, "_wgen", 0) + 1
 
     def _grad_view(self, flat_grad, name):
         off, K, C, tr, shape = self._views[name]
@@ -371,7 +383,7 @@ class _FusedQNet(nn.Module):
             ws[o:o + kpad * W] = tile(hi)
             ws[o + kpad * W:o + 2 * kpad * W] = tile(lo)
         self._wsplit = ws
-        self._wsplit_version = self._flat._version
+        self._wsplit_version = self._weights_version()
 
     def _launch_forward_layered(self, x, ei, embedding, want_argmax):
         self._ensure_packed()
@@ -380,7 +392,7 @@ class _FusedQNet(nn.Module):
         N, E = int(x.shape[0]), int(ei.shape[1])
         mode = 1 if (self.layered_gemm == "tf32x3" and net.width == 128) else 0
         if mode == 1 and (getattr(self, "_wsplit", None) is None or self._wsplit.device != x.device
-                          or self._wsplit_version != self._flat._version):
+                          or self._wsplit_version != self._weights_version()):
             self._pack_wsplit()
         L = _lib.lib()
         need = int(L.mdq_qnet_layered_workspace_bytes(net, N, E))
@@ -400,13 +412,20 @@ class _FusedQNet(nn.Module):
         _lib.check(rc, "mdq_qnet_forward_layered")
         return out, emb, am
 
-    def _use_layered(self, B, max_n):
-        return B == 1 and max_n > self.FUSED_MAX_NODES
+    def _use_layered(self, B, max_n, max_e=0):
+        """One graph that does not fit the fused kernel's shared-memory tiles (mdq_qnet_smem_bytes, host-callable)
+        goes layer by layer; batches of such graphs are not supported (loud MDQ_ESMEM from the fused launch)."""
+        if B != 1:
+            return False
+        if max_n > self.FUSED_MAX_NODES:
+            return True
+        need = int(_lib.lib().mdq_qnet_smem_bytes(self._net, int(max_n), int(max_e), 1, 0))
+        return need < 0 or need > 227 * 1024
 
     def _forward_impl(self, data, embedding=False):
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
         self._ensure_packed()
-        if self._use_layered(B, max_n):
+        if self._use_layered(B, max_n, max_e):
             if torch.is_grad_enabled() and any(p.requires_grad for _, p in self._entries):
                 raise NotImplementedError("the layered large-graph path is forward-only (Q-evaluation); wrap the call in "
                                           "torch.no_grad()")
@@ -422,7 +441,8 @@ class _FusedQNet(nn.Module):
     def select_action(self, data):
         """Fused softmax + argmax (airfoil_dqn.py:208-209): returns (action i32 [B], q [B, A])."""
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
-        if self._use_layered(B, max_n):
+        self._ensure_packed()
+        if self._use_layered(B, max_n, max_e):
             out, _, am = self._launch_forward_layered(x, ei, False, True)
             return am, out
         out, _, am = self._launch_forward(x, ei, nptr, eptr, B, max_n, max_e, False, True)

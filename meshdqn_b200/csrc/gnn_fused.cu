@@ -1745,7 +1745,7 @@ int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLa
     int rc = build_layout(*net, max_n, max_e, G, bwd, L, ck);
     if (rc == MDQ_ESMEM) {
         mdq::set_error("qnet: graphs of %d nodes / %d edges do not fit the fused kernel's shared memory tiles "
-                       "(%d graph(s)/CTA); a layered large-graph path is not built yet", max_n, max_e, G);
+                       "(%d graph(s)/CTA); a single graph of this size runs through mdq_qnet_forward_layered", max_n, max_e, G);
         return rc;
     }
     if (rc != MDQ_OK) { mdq::set_error("qnet: unsupported network/size (rc=%d)", rc); return rc; }

@@ -104,7 +104,10 @@ def train(make_env, net1, net2, *, episodes, batch_size=32, lr=1e-5, weight_deca
         state = env.get_state()
         if memory is None:
             n_feat = int(state.x.shape[1])
-            e_max = max(int(3 * env.flow_solver.mesh.nc), int(state.edge_index.shape[1]))
+            # the state graph holds only cells whose three vertices are among the N closest (Env2DAirfoil.py:259-280):
+            # 3 directed edges per such cell and <= 2 N cells among N planar points, so 6 N bounds it for every
+            # later (re-triangulated) mesh as well -- not the 3 * n_cells of the whole mesh
+            e_max = max(6 * int(state.x.shape[0]), 2 * int(state.edge_index.shape[1]))
             memory = DeviceReplayMemory(memory_capacity, int(state.x.shape[0]), e_max, n_feat, dev)
         ep_actions, ep_rewards = [], []
         t = 0

@@ -52,26 +52,31 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     return float(t.item())
 
 
-def evaluate_candidates(q_eval, candidates, rank: int, world: int, group=None):
+def evaluate_candidates(q_eval, candidates, rank: int, world: int, group=None, device=None):
     """Batched candidate-action evaluation, sharded by graph (BASELINE.json configs[4]).
 
     Candidates (one state graph per one-vertex-removed mesh variant) are independent: every rank scores its
     contiguous slice with ``q_eval(list_of_graphs) -> (best_action int [n], best_q float [n])`` (on GPU:
     ``NodeRemovalNet.select_action`` over a ``Batch``, i.e. the fused Q-kernel), and ONE ``all_gather`` of the
     per-candidate (action, q) pairs -- 8 bytes per candidate -- puts the full table on every rank.
-    Returns (actions int64 [N], q float32 [N]) in candidate order.
+    Returns (actions int64 [N], q float32 [N]) in candidate order.  ``device``: where the exchanged table lives
+    (default: the device of the candidates' ``x``); a rank whose shard is empty (N < world) must still post a
+    tensor on the collective's device (NCCL accepts CUDA tensors only).
     """
     n = len(candidates)
+    if device is None:
+        device = candidates[0].x.device if n and hasattr(candidates[0], "x") else torch.device("cpu")
+    device = torch.device(device)
     lo, hi = shard_range(n, rank, world)
     if hi > lo:
         act, q = q_eval(candidates[lo:hi])
-        local = torch.stack([act.to(torch.float32).reshape(-1), q.to(torch.float32).reshape(-1)], dim=1)
+        local = torch.stack([act.to(torch.float32).reshape(-1), q.to(torch.float32).reshape(-1)], dim=1).to(device)
     else:
-        local = torch.zeros((0, 2), dtype=torch.float32)
+        local = torch.zeros((0, 2), dtype=torch.float32, device=device)
     if world == 1:
         return local[:, 0].long(), local[:, 1]
     cap = (n + world - 1) // world                      # shard sizes differ by at most one: pad to the largest
-    buf = torch.zeros((cap, 2), dtype=torch.float32, device=local.device)
+    buf = torch.zeros((cap, 2), dtype=torch.float32, device=device)
     buf[: hi - lo] = local
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)

@@ -299,6 +299,7 @@ class ReplayTrainer:
             rc = L.mdq_adam_step(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0], self.betas[1],
                                  self.eps, self.wd, 1.0 / self.world, st["step"], _lib.stream_ptr())
         _lib.check(rc, "mdq_adam_step")
+        net._bump_weights()               # raw-pointer write: derived weight copies (TF32 hi/lo tiles) are stale now
         self.num_grads += 1
         if self.num_grads % self.target_update == 0:
             self.select = not self.select

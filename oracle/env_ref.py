@@ -60,6 +60,8 @@ class Env2DAirfoilRef:
         self.NEGATIVE_REWARD = -1.0
         self.do_nothing_offset = 0
         self.removed_coordinates = []
+        st = ap.get("interp_strict_tol", None)          # optional strict mode of SURVEY.md A.7 (Env2DAirfoil.py:569-573)
+        self.interp_strict_tol = None if st is None else float(st)
         # source mesh M0 and original fields (never updated: quirk B6)
         self.coords0 = fs.coords.copy()
         self.topo0 = fs.topo
@@ -202,9 +204,13 @@ class Env2DAirfoilRef:
     # ---- Env2DAirfoil.py:547-602 ----
     def _check_mesh(self, coords, cells):
         fs = self.flow_solver
+        old = dict(fs.__dict__)
         fs.remesh(coords, cells)
         pts = fs.topo.p2_points(fs.coords)
         cell_of, nmiss, d2 = geom.locate(pts, self.coords0, self.topo0.cells)
+        if self.interp_strict_tol is not None and nmiss and float(np.sqrt(d2.max())) > self.interp_strict_tol:
+            fs.__dict__.update(old)                     # "INTERPOLATION BROKE": old mesh back, vertex back, code 2
+            return 2
         u, p = geom.eval_fields(pts, fs.num_vertices, cell_of, self.coords0, self.topo0, self.U0, self.P0)
         self.U, self.P = u, p
         self.last.update(cell_of=cell_of, nmiss=nmiss, miss_d2=d2, pts=pts)
