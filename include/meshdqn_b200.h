@@ -89,8 +89,9 @@ int mdq_qnet_forward(const mdq_net_t *net, const float *params, const float *x, 
                      const int64_t *edge_dst, const int32_t *node_ptr, const int32_t *edge_ptr, int n_graphs,
                      int max_n, int max_e, float *out, float *embedding, int32_t *argmax, void *stream);
 
-/* Profiling aid: when set (device int64[128], NULL to disable), CTA 0 of the next qnet launches writes clock64()
- * at its phase boundaries (see MDQ_TRACE in csrc/gnn_fused.cu). */
+/* Profiling aid: when set (device int64[512], NULL to disable), CTA 0 of the next qnet launches writes clock64()
+ * at its phase boundaries (MDQ_TRACE in csrc/gnn_fused.cu: entries 0..127; STG_TRACE in csrc/gnn_staged.cuh: stage 0 at
+ * 0.., stage 1 at 32.., stage 2 at 96.., backward 1 at 256..). */
 void mdq_qnet_set_trace(int64_t *device_buf);
 
 /* Rows of (delta, input) pairs the backward kernel emits for the weight-gradient pass. */
@@ -115,6 +116,36 @@ int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const fl
                              int max_n, int max_e, int mode, const int32_t *action, const float *reward,
                              const int32_t *index, const int32_t *next_slot, const float *q_other, int batch, float gamma,
                              float *scalar, float *loss, float *grad, float *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Staged tensor-core path (csrc/gnn_staged.cuh) for NodeRemovalNet-shaped networks (SAGE, SAGE, GCN, GCN, width 128,
+ * MLP 256-128-64-out) on batches of state graphs with <= 256 nodes: the same function as mdq_qnet_forward /
+ * mdq_qnet_backward / mdq_qnet_replay_backward (same arguments, same meaning), computed as four launches whose node /
+ * MLP GEMMs run on tcgen05 as 3xTF32 (fp32 operands split hi + lo, fp32 accumulation in TMEM): Q within ~1e-6 of the
+ * fp32 kernels instead of bit-equal to them.  Replaces the same torch_geometric / nn.Linear call sites
+ * (/root/reference/airfoilgcnn.py:94-143, airfoil_dqn.py:258-305).
+ *   wsplit: mdq_qnet_staged_wsplit_floats() floats, filled by mdq_qnet_staged_wsplit() from the flat parameters and
+ *           refreshed by the caller after every weight update (one launch);
+ *   workspace: mdq_qnet_staged_workspace_floats() floats, 16-byte aligned, one per concurrent stream.
+ * ------------------------------------------------------------------------------------ */
+int mdq_qnet_staged_supported(const mdq_net_t *net, int max_n, int max_e);
+int64_t mdq_qnet_staged_wsplit_floats(const mdq_net_t *net);
+int mdq_qnet_staged_wsplit(const mdq_net_t *net, const float *params, float *wsplit, void *stream);
+int64_t mdq_qnet_staged_workspace_floats(const mdq_net_t *net, int n_graphs, int max_n, int max_e, int backward);
+int mdq_qnet_staged_forward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
+                            const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                            const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, float *out, float *embedding,
+                            int32_t *argmax, float *workspace, void *stream);
+int mdq_qnet_staged_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
+                             const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                             const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, const float *grad_out, float *grad,
+                             float *workspace, void *stream);
+int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
+                                    const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                                    const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
+                                    const int32_t *action, const float *reward, const int32_t *index,
+                                    const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
+                                    float *loss, float *grad, float *workspace, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Layered forward for ONE large graph (a state graph that does not fit the fused kernel's shared memory, e.g. the

@@ -20,6 +20,7 @@ path: tensors must live on a CUDA device.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
@@ -290,6 +291,45 @@ class _FusedQNet(nn.Module):
         nptr, eptr, B, max_n, max_e = graph_ptrs(data)
         return x, ei, nptr, eptr, B, max_n, max_e
 
+    # -- staged tensor-core path (csrc/gnn_staged.cuh): tcgen05 3xTF32 GEMMs per stage instead of one CTA per graph ----
+    qpath = os.environ.get("MDQ_QPATH", "auto")     # "auto": staged when the net / graph sizes allow it | "fused" | "staged"
+
+    def _use_staged(self, max_n, max_e):
+        if self.qpath == "fused":
+            return False
+        ok = bool(_lib.lib().mdq_qnet_staged_supported(self._net, int(max_n), int(max_e)))
+        if not ok and self.qpath == "staged":
+            raise RuntimeError("qpath='staged': this network / graph size is not served by the staged kernels")
+        return ok
+
+    def _staged_wsplit(self):
+        """hi / lo TF32 halves of every weight matrix in the staged kernels' tile layout; rebuilt (one launch) whenever
+        the weights changed."""
+        ver = self._weights_version()
+        if getattr(self, "_stg_w", None) is None or self._stg_w.device != self._flat.device or self._stg_wver != ver:
+            L = _lib.lib()
+            n = int(L.mdq_qnet_staged_wsplit_floats(self._net))
+            if getattr(self, "_stg_w", None) is None or self._stg_w.numel() != n or self._stg_w.device != self._flat.device:
+                self._stg_w = torch.empty(n, dtype=torch.float32, device=self._flat.device)
+            with torch.cuda.device(self._flat.device):
+                rc = L.mdq_qnet_staged_wsplit(self._net, _lib.ptr(self._flat), _lib.ptr(self._stg_w), _lib.stream_ptr())
+            _lib.check(rc, "mdq_qnet_staged_wsplit")
+            self._stg_wver = ver
+        return self._stg_w
+
+    def _staged_ws(self, B, max_n, max_e, backward, dev):
+        """Workspace of the staged launches, one per (stream, direction): replicas share a net across streams."""
+        need = int(_lib.lib().mdq_qnet_staged_workspace_floats(self._net, B, max_n, max_e, 1 if backward else 0))
+        if need < 0:
+            raise RuntimeError("mdq_qnet_staged_workspace_floats failed")
+        if getattr(self, "_stg_wss", None) is None:
+            self._stg_wss = {}
+        key = (torch.cuda.current_stream(dev).cuda_stream, bool(backward), dev.index)
+        ws = self._stg_wss.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._stg_wss[key] = torch.empty(need, dtype=torch.float32, device=dev)
+        return ws
+
     def _launch_forward(self, x, ei, nptr, eptr, B, max_n, max_e, embedding, want_argmax):
         self._ensure_packed()
         if self._flat.device != x.device:
@@ -304,6 +344,16 @@ class _FusedQNet(nn.Module):
         am = torch.empty((B,), dtype=torch.int32, device=x.device) if want_argmax else None
         E = int(ei.shape[1])
         L = _lib.lib()
+        if self._use_staged(max_n, max_e):
+            wsp = self._staged_wsplit()
+            ws = self._staged_ws(B, max_n, max_e, False, x.device)
+            with torch.cuda.device(x.device):
+                rc = L.mdq_qnet_staged_forward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
+                                               _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+                                               _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e, _lib.ptr(out),
+                                               _lib.ptr(emb), _lib.ptr(am), _lib.ptr(ws), _lib.stream_ptr())
+            _lib.check(rc, "mdq_qnet_staged_forward")
+            return out, emb, am
         with torch.cuda.device(x.device):
             rc = L.mdq_qnet_forward(net, _lib.ptr(self._flat), _lib.ptr(x), _lib.c_void_p(ei.data_ptr()),
                                     _lib.c_void_p(ei.data_ptr() + 8 * E), _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e,
@@ -316,6 +366,17 @@ class _FusedQNet(nn.Module):
         net = self._net
         net.x_stride = int(x.shape[1])
         L = _lib.lib()
+        if self._use_staged(max_n, max_e):
+            wsp = self._staged_wsplit()
+            ws = self._staged_ws(B, max_n, max_e, True, x.device)
+            E = int(ei.shape[1])
+            with torch.cuda.device(x.device):
+                rc = L.mdq_qnet_staged_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
+                                                _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+                                                _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e, _lib.ptr(gout),
+                                                _lib.ptr(flat_grad), _lib.ptr(ws), _lib.stream_ptr())
+            _lib.check(rc, "mdq_qnet_staged_backward")
+            return
         need = int(L.mdq_qnet_bwd_workspace_floats(net, B, max_n))
         if need < 0:
             raise RuntimeError("mdq_qnet_bwd_workspace_floats failed")
@@ -334,6 +395,20 @@ class _FusedQNet(nn.Module):
         net = self._net
         net.x_stride = int(x.shape[1])
         L = _lib.lib()
+        if self._use_staged(max_n, max_e):
+            wsp = self._staged_wsplit()
+            ws = self._staged_ws(B, max_n, max_e, True, x.device)
+            E = int(ei.shape[1])
+            with torch.cuda.device(x.device):
+                rc = L.mdq_qnet_staged_replay_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
+                                                       _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+                                                       _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e, int(mode),
+                                                       _lib.ptr(action), _lib.ptr(reward), _lib.ptr(index),
+                                                       _lib.ptr(next_slot), _lib.ptr(q_other), int(batch), float(gamma),
+                                                       _lib.ptr(scalar), _lib.ptr(loss), _lib.ptr(flat_grad), _lib.ptr(ws),
+                                                       _lib.stream_ptr())
+            _lib.check(rc, "mdq_qnet_staged_replay_backward")
+            return
         need = int(L.mdq_qnet_bwd_workspace_floats(net, B, max_n))
         if need < 0:
             raise RuntimeError("mdq_qnet_bwd_workspace_floats failed")

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include "mdq_common.cuh"
+#include "tc_prims.cuh"
 
 namespace {
 
@@ -1528,6 +1529,9 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
 constexpr int WG_ROWS = 32;   // rows per chunk: short dependent-load chains (the kernel is latency-, not FLOP-bound: ~0.1 GFLOP),
                               // the chunk partials are summed in fixed order by wgrad_reduce_kernel
 constexpr int WG_KG = 8;      // k values per thread
+constexpr int WG_SUB = 8;     // 32-row sub-chunks a task walks: 256 rows per partial (the 32-row tasks of round 1 wrote 6 MB of
+                              // partials and re-read 8 MB; the accumulators simply stay in registers across sub-chunks)
+constexpr int WG_TASK = WG_ROWS * WG_SUB;
 
 // layer li: S chunks of WG_ROWS rows, nkg groups of WG_KG k-values; partial offset = sum over earlier layers
 __device__ __forceinline__ void wg_layer_geom(const WDesc &wd, int B, int li, int &S, int &nkg, int &poff)
@@ -1536,10 +1540,10 @@ __device__ __forceinline__ void wg_layer_geom(const WDesc &wd, int B, int li, in
     for (int i = 0; i < li; ++i) {
         const int rows = B * wd.l[i].rpg;
         if (rows == 0) continue;
-        off += ((rows + WG_ROWS - 1) / WG_ROWS) * ((wd.l[i].K + 1 + WG_KG - 1) / WG_KG) * WG_KG * wd.l[i].C;
+        off += ((rows + WG_TASK - 1) / WG_TASK) * ((wd.l[i].K + 1 + WG_KG - 1) / WG_KG) * WG_KG * wd.l[i].C;
     }
     const int rows = B * wd.l[li].rpg;
-    S = (rows + WG_ROWS - 1) / WG_ROWS;
+    S = (rows + WG_TASK - 1) / WG_TASK;
     nkg = (wd.l[li].K + 1 + WG_KG - 1) / WG_KG;
     poff = off;
 }
@@ -1562,39 +1566,45 @@ __global__ void __launch_bounds__(256, 3) wgrad_partial_kernel(const WDesc wd, i
         if (t >= S * nkg) return;
         const int kg = t / S, chunk = t - kg * S;
         const int rows = B * l.rpg;
-        const int r0 = chunk * WG_ROWS, r1 = min(rows, r0 + WG_ROWS);
         const int k0 = kg * WG_KG;
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < WG_ROWS * WG_KG; idx += blockDim.x) {
-            const int rr = idx / WG_KG, j = idx - rr * WG_KG;
-            const int r = r0 + rr, k = k0 + j;
-            float v = 0.f;
-            if (r < r1) v = (k < l.K) ? __ldg(ws + l.i_off + (size_t)r * l.K + k) : (k == l.K ? 1.f : 0.f);
-            xin[rr][j] = v;
-        }
-        __syncthreads();
         float *po = partial + poff + (size_t)t * WG_KG * l.C;
-        for (int c = threadIdx.x; c < l.C; c += blockDim.x) {
-            float acc[WG_KG];
+        // C <= 256 in every layer: one column per thread, its WG_KG accumulators live across the task's sub-chunks
+        const int c = threadIdx.x;
+        float acc[WG_KG];
 #pragma unroll
-            for (int j = 0; j < WG_KG; ++j) acc[j] = 0.f;
-            const float *dl = ws + l.d_off + c;
-            const int nr = r1 - r0;
-            // all WG_ROWS delta loads of the chunk are issued together (one round trip instead of four); rows past the
-            // chunk's end contribute d = 0 against zero-filled inputs
-            float dv[WG_ROWS];
-#pragma unroll
-            for (int rr = 0; rr < WG_ROWS; ++rr) dv[rr] = rr < nr ? __ldg(dl + (size_t)(r0 + rr) * l.C) : 0.f;
-#pragma unroll
-            for (int rr = 0; rr < WG_ROWS; ++rr) {
-                const float d = dv[rr];
-                const float4 xa = *reinterpret_cast<const float4 *>(&xin[rr][0]);
-                const float4 xb = *reinterpret_cast<const float4 *>(&xin[rr][4]);
-                acc[0] = fmaf(xa.x, d, acc[0]); acc[1] = fmaf(xa.y, d, acc[1]);
-                acc[2] = fmaf(xa.z, d, acc[2]); acc[3] = fmaf(xa.w, d, acc[3]);
-                acc[4] = fmaf(xb.x, d, acc[4]); acc[5] = fmaf(xb.y, d, acc[5]);
-                acc[6] = fmaf(xb.z, d, acc[6]); acc[7] = fmaf(xb.w, d, acc[7]);
+        for (int j = 0; j < WG_KG; ++j) acc[j] = 0.f;
+        for (int sub = 0; sub < WG_SUB; ++sub) {
+            const int r0 = chunk * WG_TASK + sub * WG_ROWS, r1 = min(rows, r0 + WG_ROWS);
+            if (r0 >= rows) break;
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < WG_ROWS * WG_KG; idx += blockDim.x) {
+                const int rr = idx / WG_KG, j = idx - rr * WG_KG;
+                const int r = r0 + rr, k = k0 + j;
+                float v = 0.f;
+                if (r < r1) v = (k < l.K) ? __ldg(ws + l.i_off + (size_t)r * l.K + k) : (k == l.K ? 1.f : 0.f);
+                xin[rr][j] = v;
             }
+            __syncthreads();
+            if (c < l.C) {
+                const float *dl = ws + l.d_off + c;
+                const int nr = r1 - r0;
+                // all WG_ROWS delta loads of the sub-chunk are issued together; rows past its end contribute d = 0
+                float dv[WG_ROWS];
+#pragma unroll
+                for (int rr = 0; rr < WG_ROWS; ++rr) dv[rr] = rr < nr ? __ldg(dl + (size_t)(r0 + rr) * l.C) : 0.f;
+#pragma unroll
+                for (int rr = 0; rr < WG_ROWS; ++rr) {
+                    const float d = dv[rr];
+                    const float4 xa = *reinterpret_cast<const float4 *>(&xin[rr][0]);
+                    const float4 xb = *reinterpret_cast<const float4 *>(&xin[rr][4]);
+                    acc[0] = fmaf(xa.x, d, acc[0]); acc[1] = fmaf(xa.y, d, acc[1]);
+                    acc[2] = fmaf(xa.z, d, acc[2]); acc[3] = fmaf(xa.w, d, acc[3]);
+                    acc[4] = fmaf(xb.x, d, acc[4]); acc[5] = fmaf(xb.y, d, acc[5]);
+                    acc[6] = fmaf(xb.z, d, acc[6]); acc[7] = fmaf(xb.w, d, acc[7]);
+                }
+            }
+        }
+        if (c < l.C) {
 #pragma unroll
             for (int j = 0; j < WG_KG; ++j)
                 if (k0 + j < KB) po[(size_t)j * l.C + c] = acc[j];
@@ -1764,7 +1774,12 @@ int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLa
 
 long long *g_trace = nullptr;
 
+#include "gnn_staged.cuh"
+#include "gnn_tail.cuh"
+
 }  // namespace
+
+#include "gnn_staged_api.cuh"
 
 // ================================================================================================
 // C ABI
@@ -1848,7 +1863,7 @@ int64_t mdq_qnet_bwd_workspace_floats(const mdq_net_t *net, int n_graphs, int ma
         const WLayer &l = wd.l[i];
         if (l.rpg == 0) continue;
         const int rows = n_graphs * l.rpg;
-        const int S = (rows + WG_ROWS - 1) / WG_ROWS;
+        const int S = (rows + WG_TASK - 1) / WG_TASK;
         const int nkg = (l.K + 1 + WG_KG - 1) / WG_KG;
         partial += (int64_t)S * nkg * WG_KG * l.C;
         tasks += (int64_t)S * nkg;
@@ -1874,11 +1889,13 @@ static int qnet_backward_launch(const mdq_net_t *net, const float *params, const
         const WLayer &l = wd.l[i];
         a.wd.tstart[i] = n_tasks;
         if (l.rpg == 0) continue;
-        const int S = (n_graphs * l.rpg + WG_ROWS - 1) / WG_ROWS;
+        const int S = (n_graphs * l.rpg + WG_TASK - 1) / WG_TASK;
         const int nkg = (l.K + 1 + WG_KG - 1) / WG_KG;
         n_tasks += S * nkg;
     }
     a.wd.tstart[wd.nl] = n_tasks;
+    for (int i = 0; i < wd.nl; ++i)
+        if (wd.l[i].C > 256) { mdq::set_error("qnet backward: layers wider than 256 outputs are not supported (%d)", wd.l[i].C); return MDQ_EINVAL; }
     float *d_partial = workspace + wd.total;
     cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net->n_params * sizeof(float), st);
     if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
