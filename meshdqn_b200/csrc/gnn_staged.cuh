@@ -365,10 +365,11 @@ __global__ void __launch_bounds__(NTH, 2) k_stage0(const __grid_constant__ S0Arg
             for (int f = 0; f < FMAX; ++f)
                 if (f < F) mv[f] += xr[f];
         }
-        const float cnt = (float)(s1 - s0 > 0 ? s1 - s0 : 1);
+        const float inv = __frcp_rn((float)(s1 - s0 > 0 ? s1 - s0 : 1));   // mean = sum * (1 / deg): within 1 ulp of sum / deg
 #pragma unroll
-        for (int f = 0; f < FMAX; ++f) mv[f] = (f < F) ? mv[f] / cnt : 0.f;
+        for (int f = 0; f < FMAX; ++f) mv[f] = (f < F) ? mv[f] * inv : 0.f;
     }
+    STG_TRACE(a.trace, 0, 14);  // (profiling) means in registers
     auto write_row = [&](int r) {   // this thread's row -> row r of the A tile, hi / lo, canonical layout
         const float *xi = xs + tid * F;
         const int cm = a.Fp >> 2;
@@ -691,19 +692,21 @@ __device__ __noinline__ void gemm_main(Pipe &p, int kpad, const float *act, int 
 // [K/4][N][16 B]): no per-block barrier -- thread 0 alone walks the weight ring (wait, issue, commit), everybody else
 // goes straight to the accumulator barrier.  Measured: the per-block build / fence / __syncthreads of gemm_main cost
 // ~2.6 k cycles per block against ~0.5 k for wait + issue.
-__device__ __noinline__ void gemm_stream(Pipe &p, int kpad, const unsigned char *bfull, unsigned half_bytes, unsigned lbo_b, int N)
+__device__ __forceinline__ void gemm_stream(Pipe &p, int kpad, const unsigned char *bfull, unsigned half_bytes, unsigned lbo_b, int N)
 {
     const int tid = threadIdx.x;
     const unsigned idesc = idesc_tf32_m128(N);
     const int nkb = (kpad + KB - 1) / KB;
-    if (tid == 0) {
+    if (tid == 64) {
+        // producer: keeps the weight ring full; a stage is refilled as soon as the MMAs that read it have committed
+        p.issue_upto(p.j + (unsigned)nkb);
+    } else if (tid == 0) {
+        // MMA issuer: wait for a block, issue its 3 x (nch / 2) MMAs, commit the stage back to the producer
         const unsigned bh0 = s32(bfull), bl0 = bh0 + half_bytes;
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
             const unsigned j = p.j + (unsigned)kb;
             const int sa = (int)(j % (unsigned)p.sta);
-            p.issue_upto(j + (unsigned)p.sta - 1u);   // refills the stage of block j-2: waiting for block j-1's MMAs here
-                                                      // would expose the whole MMA latency (~2 k cycles) every block
             const int nch = min(NCH, (kpad - kb * KB) >> 2);
             mbar_wait(p.fullA + sa, (j / (unsigned)p.sta) & 1);
             tc_fence_after();
@@ -875,7 +878,6 @@ __global__ void __launch_bounds__(NTH, 1) k_stage1(const __grid_constant__ S1Arg
     STG_TRACE(a.trace, 32, 0);
     if (tid == 0) {
         p.init_barriers();
-        p.issue_upto((unsigned)p.sta);
         int r = 0, o2 = 0;
         for (int gi = 0; gi < ng; ++gi) {
             const int g = g0 + gi;
@@ -891,6 +893,7 @@ __global__ void __launch_bounds__(NTH, 1) k_stage1(const __grid_constant__ S1Arg
     __syncthreads();
     tc_fence_after();
     p.tmem = *tmem_slot;
+    if (tid == 64) p.issue_upto((unsigned)p.sta);   // the producer thread (see gemm_stream) fills the weight ring
     STG_TRACE(a.trace, 32, 1);   // set-up done
     const int NR = rb[ng];
     const int N = (NR + 15) & ~15;
@@ -922,34 +925,48 @@ __global__ void __launch_bounds__(NTH, 1) k_stage1(const __grid_constant__ S1Arg
             }
         }
     }
+    p.stamp();   // x rows stored (thread 0's share)
     for (int gi = 0; gi < ng; ++gi)
         for (int j = tid; j < ecnt[gi]; j += NTH) es1[gi * a.EC1 + j] = a.e1[(size_t)(g0 + gi) * a.EC1 + j];
+    p.stamp();   // edges copied
     __syncthreads();
-    // mean over in-edges, in edge order; warp per row, lane = 4 columns -> operand chunks 0..31 (rows >= NR: zeros)
-    for (int row = warp; row < N; row += NTH / 32) {
-        float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < NR) {
-            const int gi = graph_of(row), r = row - rb[gi];
-            const unsigned short *el = es1 + gi * a.EC1;
-            const int ne = ecnt[gi];
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            int cnt = 0;
-            for (int j = 0; j < ne; ++j) {
-                const unsigned ev = el[j];
-                if ((int)(ev >> 8) == r) {
-                    sum = f4_add(sum, *reinterpret_cast<const float4 *>(xs + (size_t)(rb[gi] + (ev & 255u)) * LDW + 4 * lane));
-                    ++cnt;
+    p.stamp();   // everyone there
+    // mean over in-edges, in edge order; half-warp per row (16 lanes x 8 columns: two rows' serial edge scans run side
+    // by side) -> operand chunks 0..31 (rows >= NR: zeros)
+    {
+        const int hl = lane & 15, hw = (tid >> 4);          // lane within the half-warp, half-warp id (0..15)
+        for (int row = hw; row < N; row += NTH / 16) {
+            float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
+            if (row < NR) {
+                const int gi = graph_of(row), r = row - rb[gi];
+                const unsigned short *el = es1 + gi * a.EC1;
+                const int ne = ecnt[gi];
+                int cnt = 0;
+                for (int j = 0; j < ne; ++j) {
+                    const unsigned ev = el[j];
+                    if ((int)(ev >> 8) == r) {
+                        const float *xr = xs + (size_t)(rb[gi] + (ev & 255u)) * LDW;
+                        m0 = f4_add(m0, *reinterpret_cast<const float4 *>(xr + 4 * hl));
+                        m1 = f4_add(m1, *reinterpret_cast<const float4 *>(xr + 64 + 4 * hl));
+                        ++cnt;
+                    }
                 }
+                const float inv = __frcp_rn((float)(cnt > 0 ? cnt : 1));   // mean = sum * (1 / deg)
+                m0 = make_float4(m0.x * inv, m0.y * inv, m0.z * inv, m0.w * inv);
+                m1 = make_float4(m1.x * inv, m1.y * inv, m1.z * inv, m1.w * inv);
             }
-            const float fc = (float)(cnt > 0 ? cnt : 1);
-            m4 = make_float4(sum.x / fc, sum.y / fc, sum.z / fc, sum.w / fc);
+            float4 h, l;
+            split_tf32(m0, h, l);
+            unsigned off = (unsigned)hl * lbo + (unsigned)row * 16u;
+            *reinterpret_cast<float4 *>(b_hi + off) = h;
+            *reinterpret_cast<float4 *>(b_lo + off) = l;
+            split_tf32(m1, h, l);
+            off += 16u * lbo;
+            *reinterpret_cast<float4 *>(b_hi + off) = h;
+            *reinterpret_cast<float4 *>(b_lo + off) = l;
         }
-        float4 h, l;
-        split_tf32(m4, h, l);
-        const unsigned off = (unsigned)lane * lbo + (unsigned)row * 16u;
-        *reinterpret_cast<float4 *>(b_hi + off) = h;
-        *reinterpret_cast<float4 *>(b_lo + off) = l;
     }
+    p.stamp();   // mean rows (thread 0's share)
     fence_async_smem();
     __syncthreads();
     STG_TRACE(a.trace, 32, 2);   // [mean | x] operand staged

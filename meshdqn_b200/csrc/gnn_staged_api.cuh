@@ -181,7 +181,7 @@ int stg_launch_tail(stg::TArgs &a, const StgGeom &G, cudaStream_t st)
     const int bytes = stg::tail_layout(a);
     int rc = stg_smem_attr(stg::k_tail<BWD>, bytes, "k_tail");
     if (rc != MDQ_OK) return rc;
-    stg::k_tail<BWD><<<(G.B + G.GS2 - 1) / G.GS2, stg::NTH, bytes, st>>>(a);
+    stg::k_tail<BWD><<<(G.B + G.GS2 - 1) / G.GS2, stg::NTH_TAIL, bytes, st>>>(a);
     return mdq::check_launch("k_tail");
 }
 
@@ -249,7 +249,7 @@ int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArg
         a.c1_d = ws + wd.l[0].d_off; a.pool1_d = ws + wd.l[4 + 0].d_off;
         const int bytes = stg::b1_layout(a);
         if ((rc = stg_smem_attr(stg::k_bwd1, bytes, "k_bwd1")) != MDQ_OK) return rc;
-        stg::k_bwd1<<<(B + G.GS1 - 1) / G.GS1, stg::NTH, bytes, st>>>(a);
+        stg::k_bwd1<<<(B + G.GS1 - 1) / G.GS1, stg::NTH_TAIL, bytes, st>>>(a);
         if ((rc = mdq::check_launch("k_bwd1")) != MDQ_OK) return rc;
     }
     wgrad_partial_kernel<<<n_tasks > 0 ? n_tasks : 1, 256, 0, st>>>(wd, B, workspace, d_partial);

@@ -71,7 +71,7 @@ struct Ring {
         __syncwarp();
         return reinterpret_cast<const float *>(base + (size_t)s * RSTAGE);
     }
-    // every thread, after its last read of the block: the warp hands the stage back; thread 0 keeps the ring full
+    // every compute thread, after its last read of the block: the warp hands the stage back to the producer warp
     __device__ __forceinline__ void release()
     {
         const int s = (int)(j % RST);
@@ -79,9 +79,14 @@ struct Ring {
         if ((threadIdx.x & 31) == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(empty + s)) : "memory");
         ++j;
-        if (threadIdx.x == 0) issue_upto(j + RST - 1);   // refills the stage released one block ago
     }
 };
+
+// The kernels below run NTH compute threads plus ONE producer warp (threads NTH..NTH+31) whose lane 0 does nothing but
+// keep the ring full (wait for a stage to come back, start its bulk copy); the compute warps never issue a copy and
+// synchronise among themselves on a named barrier.
+constexpr int NTH_TAIL = NTH + 32;
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); }
 
 // out[r][c] = sum_k act[r][k] * W[k][c] for a weight matrix of K rows (multiple of 32 rows per block, last block may be
 // short) and C columns, rows r < 8*P.  CP = C padded to 64 / 128 / 256: 256 / CP row slots, RT = 8 * CP / 256 rows per
@@ -187,7 +192,7 @@ inline int tail_layout(TArgs &a)
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a)
+__global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TArgs a)
 {
     extern __shared__ __align__(128) unsigned char sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,9 +215,13 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
     rg.full = bars; rg.empty = bars + 8; rg.base = sm + a.o_ring; rg.params = P; rg.wsplit = a.wsplit; rg.blk = a.blk; rg.nblk = a.nblk;
     rg.j = 0; rg.nissued = 0;
     STG_TRACE(a.trace, 96, 0);
+    if (tid == 0) rg.init();
+    __syncthreads();               // all NTH_TAIL threads: the barriers exist
+    if (tid >= NTH) {              // producer warp
+        if (tid == NTH) rg.issue_upto((unsigned)rg.nblk);
+        return;
+    }
     if (tid == 0) {
-        rg.init();
-        rg.issue_upto(RST);
         int r = 0;
         for (int gi = 0; gi < ng; ++gi) {
             const int g = g0 + gi;
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
     // rows past the valid ones feed discarded accumulators only, but they must not be uninitialised NaN patterns that
     // trap nothing -- they are simply never read back; zero them once so every buffer read below is defined
     for (int i = tid; i < (a.o_es - a.o_x2s) / 4; i += NTH) reinterpret_cast<float *>(sm + a.o_x2s)[i] = 0.f;
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 96, 1);
     const int N2 = rb2[ng];
     for (int idx = tid; idx < N2 * 32; idx += NTH) {
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
     }
     for (int gi = 0; gi < ng; ++gi)
         for (int j = tid; j < ecnt[gi]; j += NTH) es2[gi * a.EC2 + j] = a.e2[(size_t)(g0 + gi) * a.EC2 + j];
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 96, 2);   // inputs loaded
     const int c128 = tid & 127, half = tid >> 7;
     // ---- block 2: GCNConv (conv4): XW = X2 . W4, then A_hat ----
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
         }
         dis[tid] = __fdiv_rn(1.f, __fsqrt_rn((float)deg));
     }
-    __syncthreads();
+    cta_sync();
     for (int row = warp; row < N2; row += NTH / 32) {
         const int gi = rowg[row], r = row - rb2[gi];
         const unsigned short *el = es2 + gi * a.EC2;
@@ -287,16 +296,16 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
         *reinterpret_cast<float4 *>(H3 + (size_t)row * LDW + 4 * lane) =
             make_float4(fmaxf(sum.x, 0.f), fmaxf(sum.y, 0.f), fmaxf(sum.z, 0.f), fmaxf(sum.w, 0.f));
     }
-    __syncthreads();
+    cta_sync();
     row_scores(H3, LDW, N2, P + a.p4_off, score3, z3);
-    __syncthreads();
+    cta_sync();
     if (tid < ng) {   // TopK with one survivor: highest score, ties -> lower index
         int best = rb2[tid];
         for (int j = rb2[tid] + 1; j < rb2[tid + 1]; ++j)
             if (score3[j] > score3[best]) best = j;
         sel3[tid] = best - rb2[tid];
     }
-    __syncthreads();
+    cta_sync();
     for (int idx = tid; idx < ng * 128; idx += NTH) {
         const int gi = idx >> 7, c = idx & 127;
         const int i = rb2[gi] + sel3[gi];
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
         X3s[gi * LDW + c] = v;
         a.x3[(size_t)(g0 + gi) * 128 + c] = v;
     }
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 96, 3);   // block 2 done
     // ---- block 3: GCNConv (conv5) on the single remaining node: A_hat = [1] ----
     {
@@ -317,9 +326,9 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
             if (r < ng) H4[r * LDW + c128] = fmaxf(acc[0][q] + bm, 0.f);
         }
     }
-    __syncthreads();
+    cta_sync();
     row_scores(H4, LDW, ng, P + a.p5_off, s4, z4);
-    __syncthreads();
+    cta_sync();
     // ---- readout: x1 + x2 + x4 + x5 (airfoilgcnn.py:134), each [max | mean] over its kept rows ----
     for (int idx = tid; idx < ng * 256; idx += NTH) {
         const int gi = idx >> 8, c = idx & 255, cc = c & 127;
@@ -329,7 +338,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
         if (a.emb) a.emb[go] = v;
         if (BWD) a.lin_in[0][go] = v;
     }
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 96, 4);   // block 3 + readout sum
     // ---- MLP ----
     {
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
             }
         }
     }
-    __syncthreads();
+    cta_sync();
     {
         float acc[1][2];
         dense_fwd<64, 1>(rg, 128, 64, y1, LDW, 1, acc);
@@ -362,7 +371,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
             }
         }
     }
-    __syncthreads();
+    cta_sync();
     {
         float acc[1][8];
         dense_fwd<256, 1>(rg, 64, A, y2, LDY2, 1, acc);
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                 if (q < ng) y3[q * LDY3 + tid] = acc[0][q] + bm;
         }
     }
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 96, 5);   // MLP
     // ---- softmax, argmax (first maximum) ----
     for (int gi = warp; gi < ng; gi += NTH / 32) {
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
         __syncwarp();
         for (int c = lane; c < A; c += 32) a.lin_d[2][(size_t)g * A + c] = y[c];
     }
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 96, 6);   // softmax / loss gradient
     if (BWD) {
         // ---- MLP backward on the transposed weight copies: d2 = (d3.W3^T) relu'(y2), d1 = (d2.W2^T) relu'(y1), dR = d1.W1^T ----
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                 }
             }
         }
-        __syncthreads();
+        cta_sync();
         {
             float acc[1][4];
             dense_fwd<128, 1>(rg, 64, 128, y2, LDY2, 1, acc);
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                 }
             }
         }
-        __syncthreads();
+        cta_sync();
         {
             float acc[1][8];
             dense_fwd<256, 1>(rg, 128, 256, y1, LDW, 1, acc);
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                     a.dR[(size_t)(g0 + q) * 256 + tid] = acc[0][q];
                 }
         }
-        __syncthreads();
+        cta_sync();
         // ---- block 3 backward: one row per graph, warp per graph ----
         {
             const float4 w = __ldg(reinterpret_cast<const float4 *>(P + a.p5_off) + lane);
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                 *reinterpret_cast<float4 *>(a.pool5_d + go) = dpool;
             }
         }
-        __syncthreads();
+        cta_sync();
         {
             float acc[1][4];
             dense_fwd<128, 1>(rg, 128, 128, H4, LDW, 1, acc);
@@ -531,7 +540,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                 if (r < ng) X3s[r * LDW + c128] = acc[0][q];
             }
         }
-        __syncthreads();
+        cta_sync();
         // ---- block 2 backward: pooling through the one kept row, then A_hat^T ----
         {
             const float4 w = __ldg(reinterpret_cast<const float4 *>(P + a.p4_off) + lane);
@@ -570,7 +579,7 @@ __global__ void __launch_bounds__(NTH, 1) k_tail(const __grid_constant__ TArgs a
                 }
             }
         }
-        __syncthreads();
+        cta_sync();
         {
             float acc[4][4];
             dense_fwd<128, 4>(rg, 128, 128, XW, LDW, (N2 + 7) >> 3, acc);
@@ -631,7 +640,7 @@ inline int b1_layout(B1Args &a)
     return o;
 }
 
-__global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args a)
+__global__ void __launch_bounds__(NTH_TAIL, 1) k_bwd1(const __grid_constant__ B1Args a)
 {
     extern __shared__ __align__(128) unsigned char sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -655,9 +664,13 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
     rg.full = bars; rg.empty = bars + 8; rg.base = sm + a.o_ring; rg.params = P; rg.wsplit = a.wsplit; rg.blk = a.blk; rg.nblk = a.nblk;
     rg.j = 0; rg.nissued = 0;
     STG_TRACE(a.trace, 256, 0);
+    if (tid == 0) rg.init();
+    __syncthreads();               // all NTH_TAIL threads: the barriers exist
+    if (tid >= NTH) {              // producer warp
+        if (tid == NTH) rg.issue_upto((unsigned)rg.nblk);
+        return;
+    }
     if (tid == 0) {
-        rg.init();
-        rg.issue_upto(RST);
         int r = 0, o2 = 0;
         for (int gi = 0; gi < ng; ++gi) {
             const int g = g0 + gi;
@@ -669,7 +682,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
         rb1[ng] = r; ob2[ng] = o2;
     }
     for (int i = tid; i < nk2m * LDW; i += NTH) dP2[i] = 0.f;   // rows past NK2 are read (and discarded) by the GEMM
-    __syncthreads();
+    cta_sync();
     const int NK2 = ob2[ng], NR1 = rb1[ng];
     // ---- everything this CTA needs from global memory, issued together (one latency, not one per use) ----
     for (int idx = tid; idx < NR1 * 32; idx += NTH) {     // block 0's kept hidden rows
@@ -710,7 +723,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
     }
     for (int gi = 0; gi < ng; ++gi)
         for (int j = tid; j < ecnt[gi]; j += NTH) es1[gi * a.EC1 + j] = a.e1[(size_t)(g0 + gi) * a.EC1 + j];
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 256, 1);  // inputs staged
     // ---- block 1 pooling backward: warp per kept row; the pool-weight terms are summed per graph in row order below ----
     {
@@ -737,7 +750,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
             *reinterpret_cast<float4 *>(pt2 + (size_t)row * LDW + 4 * lane) = term;
         }
     }
-    __syncthreads();
+    cta_sync();
     for (int idx = tid; idx < ng * R2 * 32; idx += NTH) {   // conv2's delta rows (zeros past the kept rows)
         const int gi = idx / (R2 * 32), rem = idx - gi * R2 * 32, r = rem >> 5, c4 = rem & 31;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -760,7 +773,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
         for (int e = 0; e < ecnt[gi]; ++e) d += ((int)(el[e] >> 8) == i);
         deg[tid] = d;
     }
-    __syncthreads();             // H2 / pt2 (aliasing dcat) are dead from here
+    cta_sync();             // H2 / pt2 (aliasing dcat) are dead from here
     STG_TRACE(a.trace, 256, 2);  // block 1 pooling backward
     // ---- dcat = dP2 . W2^T on the transposed copy (rows = the 128 outputs of conv2, 256 columns = [mean | x] inputs) ----
     {
@@ -772,7 +785,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
             for (int q = 0; q < 8; ++q)
                 if (p * 8 + q < NK2) dcat[(size_t)(p * 8 + q) * LD2W + tid] = acc[p][q];
     }
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 256, 3);  // conv2^T
     // ---- dX1: the x half goes to the row itself, the mean half to its in-neighbours / in-degree; warp per level-1 row ----
     for (int row = warp; row < NR1; row += NTH / 32) {
@@ -797,7 +810,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
         }
         *reinterpret_cast<float4 *>(dX1 + (size_t)row * LDW + 4 * lane) = acc;
     }
-    __syncthreads();
+    cta_sync();
     STG_TRACE(a.trace, 256, 4);  // dX1
     // ---- block 0 pooling backward: warp per kept row; the pool-weight partial is summed per graph afterwards ----
     const float4 w1 = __ldg(reinterpret_cast<const float4 *>(P + a.p1_off) + lane);
@@ -829,7 +842,7 @@ __global__ void __launch_bounds__(NTH, 1) k_bwd1(const __grid_constant__ B1Args 
         }
         *reinterpret_cast<float4 *>(a.c1_d + ((size_t)g * R1 + r) * 128 + 4 * lane) = dp;
     }
-    __syncthreads();
+    cta_sync();
     for (int idx = tid; idx < ng * 128; idx += NTH) {
         const int gi = idx >> 7, c = idx & 127;
         const float wc = __ldg(P + a.p1_off + c);

@@ -16,7 +16,7 @@ for _ in range(2):
     net = NodeRemovalNet(181, 128, 0.1); net.set_num_nodes(17); net = net.to(dev); net.qpath = "staged"; nets.append(net)
 net = nets[0]
 S0 = ["start", "x loaded, TMEM", "edges counted", "scan", "fill", "sort", "A tile 0", "W1 landed", "tile0 MMA done", "tile1 done",
-      "scores", "ranked", "kept rows+filter", "outputs"]
+      "scores", "ranked", "kept rows+filter", "outputs", "(means in regs: absolute)"]
 S1 = ["start", "setup", "cat2 built", "GEMM+epi", "scores", "outputs"]
 S2 = ["start", "setup", "inputs", "block2", "block3+readout", "MLP", "softmax/lossgrad", "end"]
 B1 = ["start", "inputs staged", "pool2 bwd", "conv2T", "dX1", "pool1 bwd (end)"]
@@ -36,6 +36,11 @@ def dump(t, base, names, pipe_base=None, pipe_end=None):
 
 
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+NOFLUSH = "--noflush" in sys.argv
+_fill = flush.fill_
+if NOFLUSH:
+    flush.fill_ = lambda v: None
+    print("*** L2 NOT flushed between runs")
 for B in (1, 256):
     b = Batch.from_data_list([mk() for _ in range(B)]).to(dev)
     tr = torch.zeros(512, dtype=torch.int64, device=dev)
