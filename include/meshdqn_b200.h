@@ -145,7 +145,11 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
                                     const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
                                     const int32_t *action, const float *reward, const int32_t *index,
                                     const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
-                                    float *loss, float *grad, float *workspace, void *stream);
+                                    float *loss, float *grad, float *workspace, int phase, void *stream);
+/* mdq_qnet_staged_replay_backward differs from mdq_qnet_replay_backward in two ways: the flat gradient's entries of
+ * blocks the forward never uses are left untouched (keep a persistent zero-initialised buffer), and `phase` splits the
+ * call -- 0: everything; 1: stages 0 / 1 of the selected net only (they do not read q_other, so they may be enqueued on
+ * a second stream beside the other net's forward); 2: the remaining launches (same arguments, same workspace). */
 
 /* ------------------------------------------------------------------------------------
  * Layered forward for ONE large graph (a state graph that does not fit the fused kernel's shared memory, e.g. the

@@ -317,14 +317,15 @@ class _FusedQNet(nn.Module):
             self._stg_wver = ver
         return self._stg_w
 
-    def _staged_ws(self, B, max_n, max_e, backward, dev):
-        """Workspace of the staged launches, one per (stream, direction): replicas share a net across streams."""
+    def _staged_ws(self, B, max_n, max_e, backward, dev, shared=False):
+        """Workspace of the staged launches, one per (stream, direction): replicas share a net across streams.
+        ``shared``: one workspace whatever the stream (the two phases of the replay backward run on two streams)."""
         need = int(_lib.lib().mdq_qnet_staged_workspace_floats(self._net, B, max_n, max_e, 1 if backward else 0))
         if need < 0:
             raise RuntimeError("mdq_qnet_staged_workspace_floats failed")
         if getattr(self, "_stg_wss", None) is None:
             self._stg_wss = {}
-        key = (torch.cuda.current_stream(dev).cuda_stream, bool(backward), dev.index)
+        key = (0 if shared else torch.cuda.current_stream(dev).cuda_stream, bool(backward), dev.index)
         ws = self._stg_wss.get(key)
         if ws is None or ws.numel() < need:
             ws = self._stg_wss[key] = torch.empty(need, dtype=torch.float32, device=dev)
@@ -390,14 +391,14 @@ class _FusedQNet(nn.Module):
         _lib.check(rc, "mdq_qnet_backward")
 
     def _launch_replay_backward(self, x, ei, nptr, eptr, B, max_n, max_e, mode, action, reward, index, next_slot, q_other,
-                                batch, gamma, scalar, loss, flat_grad):
+                                batch, gamma, scalar, loss, flat_grad, phase=0):
         self._ensure_packed()
         net = self._net
         net.x_stride = int(x.shape[1])
         L = _lib.lib()
         if self._use_staged(max_n, max_e):
             wsp = self._staged_wsplit()
-            ws = self._staged_ws(B, max_n, max_e, True, x.device)
+            ws = self._staged_ws(B, max_n, max_e, True, x.device, shared=True)
             E = int(ei.shape[1])
             with torch.cuda.device(x.device):
                 rc = L.mdq_qnet_staged_replay_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
@@ -406,9 +407,12 @@ class _FusedQNet(nn.Module):
                                                        _lib.ptr(action), _lib.ptr(reward), _lib.ptr(index),
                                                        _lib.ptr(next_slot), _lib.ptr(q_other), int(batch), float(gamma),
                                                        _lib.ptr(scalar), _lib.ptr(loss), _lib.ptr(flat_grad), _lib.ptr(ws),
-                                                       _lib.stream_ptr())
+                                                       int(phase), _lib.stream_ptr())
             _lib.check(rc, "mdq_qnet_staged_replay_backward")
             return
+        if phase == 1:
+            return      # the fused kernel has no split: everything happens in the finishing call
+
         need = int(L.mdq_qnet_bwd_workspace_floats(net, B, max_n))
         if need < 0:
             raise RuntimeError("mdq_qnet_bwd_workspace_floats failed")

@@ -9,7 +9,7 @@ struct StgWs {
     float *x1, *r0, *r1, *x2, *x3;
     unsigned short *e1, *e2;
     int *e1n, *e2n;
-    float *h1k, *s1k, *z1k, *h2k, *s2k, *z2k, *dX2, *dR;
+    float *h1k, *s1k, *z1k, *h2k, *s2k, *z2k, *dX2, *dR, *lterm;
     unsigned char *amax1, *amax2, *perm2;
     int64_t floats;
 };
@@ -50,7 +50,7 @@ void stg_carve(const StgGeom &G, float *base, bool bwd, StgWs &w)
     if (!bwd) {
         w.x2 = takef(B * G.R2 * 128);
         w.x3 = takef(B * 128);
-        w.h1k = w.s1k = w.z1k = w.h2k = w.s2k = w.z2k = w.dX2 = w.dR = nullptr;
+        w.h1k = w.s1k = w.z1k = w.h2k = w.s2k = w.z2k = w.dX2 = w.dR = w.lterm = nullptr;
         w.amax1 = w.amax2 = w.perm2 = nullptr;
     } else {
         w.x2 = w.x3 = nullptr;
@@ -62,6 +62,7 @@ void stg_carve(const StgGeom &G, float *base, bool bwd, StgWs &w)
         w.z2k = takef(B * G.R2);
         w.dX2 = takef(B * G.R2 * 128);
         w.dR = takef(B * 256);
+        w.lterm = takef(B);
         w.amax1 = reinterpret_cast<unsigned char *>(takef(B * 32));
         w.amax2 = reinterpret_cast<unsigned char *>(takef(B * 32));
         w.perm2 = reinterpret_cast<unsigned char *>(takef((B * G.R2 + 3) / 4));
@@ -185,8 +186,12 @@ int stg_launch_tail(stg::TArgs &a, const StgGeom &G, cudaStream_t st)
     return mdq::check_launch("k_tail");
 }
 
+// phase 0: everything; 1: stages 0 / 1 only (independent of Q_other: may run beside the other net's forward);
+// 2: the rest (tail backward, backward 1, weight gradients).  zero_grad: memset the flat gradient first (the unused
+// blocks' entries); the replay path keeps a persistent, pre-zeroed gradient buffer instead.
+struct StgLoss { int batch; const int32_t *next_slot; float *loss; };
 int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArgs &a2, float *grad, float *workspace,
-                        cudaStream_t st)
+                        cudaStream_t st, int phase, bool zero_grad, const StgLoss &ls)
 {
     const mdq_net_t &net = *c.net;
     if (!stg::supported(net, max_n, max_e)) { mdq::set_error("staged path: unsupported network / graph size"); return MDQ_EINVAL; }
@@ -215,17 +220,22 @@ int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArg
     StgWs w;
     stg_carve(G, workspace + ((fused_ws + 3) & ~(int64_t)3), true, w);
     float *ws = workspace;
-    cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net.n_params * sizeof(float), st);
-    if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
+    if (zero_grad && phase != 2) {
+        cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net.n_params * sizeof(float), st);
+        if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
+    }
     float *x2 = ws + wd.l[2].i_off, *x3 = ws + wd.l[3].i_off;
-    int rc = stg_launch_01<true>(c, G, P, w, ws + wd.l[0].i_off, ws + wd.l[1].i_off, x2, st);
-    if (rc != MDQ_OK) return rc;
+    int rc = MDQ_OK;
+    if (phase != 2) {
+        rc = stg_launch_01<true>(c, G, P, w, ws + wd.l[0].i_off, ws + wd.l[1].i_off, x2, st);
+        if (rc != MDQ_OK || phase == 1) return rc;
+    }
     {
         stg::TArgs keep = a2;   // the caller filled the loss-gradient fields
         stg_tail_common(a2, c, G, P, w, x2, x3, true);
         a2.mode = keep.mode; a2.gout = keep.gout; a2.rp_action = keep.rp_action; a2.rp_reward = keep.rp_reward;
         a2.rp_index = keep.rp_index; a2.rp_qother = keep.rp_qother; a2.rp_gamma = keep.rp_gamma;
-        a2.rp_inv_batch = keep.rp_inv_batch; a2.rp_scalar = keep.rp_scalar;
+        a2.rp_inv_batch = keep.rp_inv_batch; a2.rp_scalar = keep.rp_scalar; a2.lterm = w.lterm;
         const int nb = 4;
         for (int i = 0; i < 3; ++i) { a2.lin_in[i] = ws + wd.l[2 * nb + i].i_off; a2.lin_d[i] = ws + wd.l[2 * nb + i].d_off; }
         a2.c5_d = ws + wd.l[3].d_off; a2.c4_d = ws + wd.l[2].d_off;
@@ -247,6 +257,8 @@ int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArg
         a.h1k = w.h1k; a.s1k = w.s1k; a.z1k = w.z1k; a.amax1 = w.amax1;
         a.c2_d = ws + wd.l[1].d_off; a.pool2_d = ws + wd.l[4 + 1].d_off;
         a.c1_d = ws + wd.l[0].d_off; a.pool1_d = ws + wd.l[4 + 0].d_off;
+        a.mode = a2.mode; a.batch = ls.batch; a.A = net.out_dim; a.lterm = w.lterm; a.rp_qother = a2.rp_qother;
+        a.rp_reward = a2.rp_reward; a.rp_action = a2.rp_action; a.next_slot = ls.next_slot; a.loss = ls.loss;
         const int bytes = stg::b1_layout(a);
         if ((rc = stg_smem_attr(stg::k_bwd1, bytes, "k_bwd1")) != MDQ_OK) return rc;
         stg::k_bwd1<<<(B + G.GS1 - 1) / G.GS1, stg::NTH_TAIL, bytes, st>>>(a);
@@ -344,7 +356,7 @@ int mdq_qnet_staged_backward(const mdq_net_t *net, const float *params, const fl
     stg::TArgs a2;
     memset(&a2, 0, sizeof(a2));
     a2.mode = 0; a2.gout = grad_out;
-    return stg_backward_launch(c, n_graphs, max_n, max_e, a2, grad, workspace, (cudaStream_t)stream);
+    return stg_backward_launch(c, n_graphs, max_n, max_e, a2, grad, workspace, (cudaStream_t)stream, 0, true, StgLoss{0, nullptr, nullptr});
 }
 
 int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
@@ -352,11 +364,11 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
                                     const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
                                     const int32_t *action, const float *reward, const int32_t *index,
                                     const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
-                                    float *loss, float *grad, float *workspace, void *stream)
+                                    float *loss, float *grad, float *workspace, int phase, void *stream)
 {
     if (!net || !params || !wsplit || !x || !grad || !workspace || !action || !reward || !index || !next_slot || !scalar ||
-        !loss || n_graphs < 1 || batch < 1 || (mode != 1 && mode != 2) || (mode == 2 && !q_other) ||
-        (reinterpret_cast<uintptr_t>(workspace) & 15)) {
+        !loss || n_graphs < 1 || batch < 1 || (mode != 1 && mode != 2) || (mode == 2 && phase != 1 && !q_other) ||
+        phase < 0 || phase > 2 || (reinterpret_cast<uintptr_t>(workspace) & 15)) {
         mdq::set_error("mdq_qnet_staged_replay_backward: bad argument");
         return MDQ_EINVAL;
     }
@@ -365,11 +377,8 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
     memset(&a2, 0, sizeof(a2));
     a2.mode = mode; a2.rp_action = action; a2.rp_reward = reward; a2.rp_index = index; a2.rp_qother = q_other;
     a2.rp_gamma = gamma; a2.rp_inv_batch = 1.f / (float)batch; a2.rp_scalar = scalar;
-    int rc = stg_backward_launch(c, n_graphs, max_n, max_e, a2, grad, workspace, (cudaStream_t)stream);
-    if (rc != MDQ_OK) return rc;
-    replay_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mode, scalar, q_other, action, reward, next_slot, batch,
-                                                           net->out_dim, gamma, loss);
-    return mdq::check_launch("replay_loss_kernel");
+    return stg_backward_launch(c, n_graphs, max_n, max_e, a2, grad, workspace, (cudaStream_t)stream, phase, false,
+                               StgLoss{batch, next_slot, loss});
 }
 
 }  // extern "C"

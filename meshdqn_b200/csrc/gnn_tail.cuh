@@ -163,10 +163,11 @@ struct TArgs {
     const float *rp_qother;
     float rp_gamma, rp_inv_batch;
     float *rp_scalar;
+    float *lterm;                 // [n_graphs] Huber term of each graph's transition (modes 1 / 2); summed by k_bwd1
     float *lin_in[3], *lin_d[3];  // weight-gradient rows: inputs Rs / y1 / y2, deltas d1 / d2 / d3
     float *c5_d, *c4_d, *pool4_d, *pool5_d, *bias4_d, *bias5_d;
     float *dX2, *dR;              // [B][R2][128], [B][256]
-    int o_ring, o_x2s, o_xw, o_x3s, o_h4, o_rs, o_y1, o_y2, o_y3, o_es, o_int, o_f, o_rowg, total;
+    int o_ring, o_x2s, o_xw, o_x3s, o_h4, o_rs, o_y1, o_y2, o_y3, o_es, o_int, o_f, o_rowg, o_lg, total;
 };
 
 inline int tail_layout(TArgs &a)
@@ -187,6 +188,7 @@ inline int tail_layout(TArgs &a)
     a.o_int = take((4 * a.GS + 2) * 4);
     a.o_f = take((3 * n2m + 2 * a.GS) * 4);
     a.o_rowg = take(n2m);
+    a.o_lg = take(a.GS * 4 * 4);        // loss-gradient inputs fetched at kernel start: sel, pred, nsv, rew per graph
     a.total = o;
     return o;
 }
@@ -248,6 +250,38 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
     }
     for (int gi = 0; gi < ng; ++gi)
         for (int j = tid; j < ecnt[gi]; j += NTH) es2[gi * a.EC2 + j] = a.e2[(size_t)(g0 + gi) * a.EC2 + j];
+    float *lgf = reinterpret_cast<float *>(sm + a.o_lg);   // [GS][4]: sel (as int bits), pred, nsv, rew
+    if (BWD && a.mode != 0) {
+        // the transition data and Q_other row of each graph: fetched now so that their (cold) latency hides under the forward chain
+        for (int gi = warp; gi < ng; gi += NTH / 32) {
+            const int g = g0 + gi;
+            int sel = 0;
+            float pred = 0.f, nsv = 0.f, rew;
+            if (a.mode == 1) {
+                sel = a.rp_action[g];
+                rew = a.rp_reward[g];
+                const int slot = a.rp_index[g];
+                float m = -INFINITY;
+                if (slot >= 0) {
+                    const float *q = a.rp_qother + (size_t)slot * A;
+                    for (int c = lane; c < A; c += 32) m = fmaxf(m, __ldg(q + c));
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+                }
+                nsv = slot >= 0 ? m : 0.f;
+            } else {
+                const int b = a.rp_index[g];
+                pred = __ldg(a.rp_qother + (size_t)b * A + a.rp_action[b]);
+                rew = a.rp_reward[b];
+            }
+            if (lane == 0) {
+                lgf[gi * 4] = __int_as_float(sel);
+                lgf[gi * 4 + 1] = pred;
+                lgf[gi * 4 + 2] = nsv;
+                lgf[gi * 4 + 3] = rew;
+            }
+        }
+    }
     cta_sync();
     STG_TRACE(a.trace, 96, 2);   // inputs loaded
     const int c128 = tid & 127, half = tid >> 7;
@@ -431,32 +465,20 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
                 y[c] = a.softmax ? y[c] * (gc - dot) : gc;
             }
         } else {
-            int sel;
-            float pred, nsv, rew;
+            int sel = __float_as_int(lgf[gi * 4]);
+            float pred = lgf[gi * 4 + 1], nsv = lgf[gi * 4 + 2];
+            const float rew = lgf[gi * 4 + 3];
             if (a.mode == 1) {
-                sel = a.rp_action[g];
                 pred = y[sel];
-                rew = a.rp_reward[g];
-                const int slot = a.rp_index[g];
-                float m = -INFINITY;
-                if (slot >= 0) {
-                    const float *q = a.rp_qother + (size_t)slot * A;
-                    for (int c = lane; c < A; c += 32) m = fmaxf(m, __ldg(q + c));
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
-                }
-                nsv = slot >= 0 ? m : 0.f;
                 if (lane == 0) a.rp_scalar[g] = pred;
             } else {
-                const int b = a.rp_index[g];
-                pred = __ldg(a.rp_qother + (size_t)b * A + a.rp_action[b]);
-                rew = a.rp_reward[b];
                 sel = bi;
                 nsv = bv;
                 if (lane == 0) a.rp_scalar[g] = bv;
             }
             const float d = pred - (nsv * a.rp_gamma + rew);
             const float hd = (fabsf(d) < 1.f) ? d : (d > 0.f ? 1.f : -1.f);
+            if (lane == 0) a.lterm[g] = (fabsf(d) < 1.f) ? 0.5f * d * d : (fabsf(d) - 0.5f);
             const float gsel = (a.mode == 1) ? hd * a.rp_inv_batch : -hd * a.rp_gamma * a.rp_inv_batch;
             const float ysel = y[sel];
             __syncwarp();
@@ -618,6 +640,12 @@ struct B1Args {
     const unsigned char *amax1;
     float *c2_d, *pool2_d;         // weight-gradient deltas of conv2 [B*R2][128], pool2 [B][128]
     float *c1_d, *pool1_d;         // ... of conv1 [B*R1][128], pool1 [B][128]
+    // loss = mean Huber over the `batch` transitions: the graphs' terms come from k_tail (lterm), mode 2 adds the terminal
+    // transitions (no next-state graph); summed by CTA 0 in a fixed order.  mode 0: no loss.
+    int mode, batch, A;
+    const float *lterm, *rp_qother, *rp_reward;
+    const int *rp_action, *next_slot;
+    float *loss;
     int o_ring, o_dp2, o_dcat, o_dx1, o_h1, o_dr, o_am, o_es, o_int, o_f, total;
 };
 
@@ -853,6 +881,25 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_bwd1(const __grid_constant__ B1
             acc += tds0[lr] * (H1[(size_t)lr * LDW + c] / wn1 - z1[lr] * wc / wn2);
         }
         a.pool1_d[(size_t)(g0 + gi) * 128 + c] = acc;
+    }
+    if (a.mode != 0 && blockIdx.x == 0) {
+        cta_sync();
+        float *red = dX1;   // scratch: dX1 is dead
+        float sum = 0.f;
+        for (int g = tid; g < a.B; g += NTH) sum += a.lterm[g];
+        if (a.mode == 2)
+            for (int b = tid; b < a.batch; b += NTH)
+                if (a.next_slot[b] < 0) {
+                    const float d = a.rp_qother[(size_t)b * a.A + a.rp_action[b]] - a.rp_reward[b];
+                    sum += (fabsf(d) < 1.f) ? 0.5f * d * d : (fabsf(d) - 0.5f);
+                }
+        red[tid] = sum;
+        cta_sync();
+        for (int o = NTH / 2; o; o >>= 1) {
+            if (tid < o) red[tid] += red[tid + o];
+            cta_sync();
+        }
+        if (tid == 0) *a.loss = red[0] / (float)a.batch;
     }
     STG_TRACE(a.trace, 256, 5);  // end
 }

@@ -204,6 +204,8 @@ class ReplayTrainer:
         self.num_grads = 0
         self._state = [None, None]
         self.timers = None  # optional {name: [(start_event, end_event), ...]} for per-kernel timing
+        self.overlap = True  # selected net's first stages on a side stream beside the other net's forward
+        self._side = None
 
     # -- helpers ----------------------------------------------------------------------------
     def _adam_state(self, i):
@@ -256,20 +258,32 @@ class ReplayTrainer:
         A = net._net.out_dim
         if fused and (self.select or n_args is not None):
             if self.select:
-                q_other = None
-                if n_args is not None:
-                    with self._timed("qnet_fwd"):
-                        q_other, _, _ = net2._launch_forward(*n_args, False, False)
                 args, mode, index = s_args, 1, batch.next_slot
+                other, o_args = net2, n_args
             else:
-                with self._timed("qnet_fwd"):
-                    q_other, _, _ = net1._launch_forward(*s_args, False, False)
-                args, mode = n_args, 2
-                index = batch.owner
+                args, mode, index = n_args, 2, batch.owner
+                other, o_args = net1, s_args
             scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
+            # The selected net's stages 0 / 1 do not read Q_other: they go to a second stream and run beside the other
+            # net's forward, whose tail occupies few SMs (staged path only; the fused kernel does everything in phase 2).
+            overlap = self.overlap and o_args is not None and self.timers is None
+            if overlap:
+                main = torch.cuda.current_stream(dev)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(dev)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    net._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, None, B,
+                                                self.gamma, scalar, loss, st["g"], phase=1)
+            q_other = None
+            if o_args is not None:
+                with self._timed("qnet_fwd"):
+                    q_other, _, _ = other._launch_forward(*o_args, False, False)
+            if overlap:
+                main.wait_stream(self._side)
             with self._timed("qnet_bwd+wgrad"):
                 net._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, q_other, B,
-                                            self.gamma, scalar, loss, st["g"])
+                                            self.gamma, scalar, loss, st["g"], phase=2 if overlap else 0)
         else:
             with self._timed("qnet_fwd"):
                 q1, _, _ = net1._launch_forward(*s_args, False, False)
