@@ -215,7 +215,7 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
 
     tr = random_transitions(BATCH, 1000 + rank) if args.fast_setup else harvest_transitions(env_factory(dev), BATCH, 1000 + rank)
-    rb_host = ReplayBatch.from_transitions(tr).pin_memory()
+    rb_host = ReplayBatch.from_transitions(tr).pin_memory(slim=True)   # features + 32-bit edges + 32-bit offsets only
     rb_dev = rb_host.to(dev)
     torch.manual_seed(1370)
     nets = []
@@ -223,7 +223,8 @@ def run_ours(args):
         n = NodeRemovalNet(181, conv_width=128, topk=0.1)
         n.set_num_nodes(17)
         nets.append(n.to(dev))
-    trainer = ReplayTrainer(nets[0], nets[1], lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50)
+    # graphs=True: the step's launches are captured once per (select branch, minibatch buffers) and replayed
+    trainer = ReplayTrainer(nets[0], nets[1], lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50, graphs=not args.no_graphs)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -261,7 +262,7 @@ def run_ours(args):
     # step k+1 runs on a side stream while step k computes (DevicePrefetcher), and the loss of step k is read (pinned
     # D2H + event) while step k+1 is already enqueued -- the public training-loop API a user would call ----
     from meshdqn_b200.replay import DevicePrefetcher
-    pf = DevicePrefetcher(dev)
+    pf = DevicePrefetcher(dev, static=True)   # two persistent device arenas: fixed addresses for the captured step
     loss_host = torch.zeros(K + 4, dtype=torch.float32).pin_memory()
 
     def e2e_loop(n):
@@ -272,6 +273,7 @@ def run_ours(args):
             if k + 1 < n:
                 pf.submit(rb_host)
             loss = trainer.step(rb)
+            pf.release()
             loss_host[k:k + 1].copy_(loss, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
@@ -281,7 +283,7 @@ def run_ours(args):
                 float(loss_host[k - 1])
         evs[-1].synchronize()
         return float(loss_host[n - 1])
-    e2e_loop(3)
+    e2e_loop(8)      # covers the capture of the step on both arenas
     barrier()
     t0 = time.perf_counter()
     e2e_loop(K)
@@ -626,6 +628,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--fast-setup", action="store_true", help="random graphs instead of harvested transitions (profiler runs only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

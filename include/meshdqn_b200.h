@@ -126,22 +126,24 @@ int mdq_qnet_replay_backward(const mdq_net_t *net, const float *params, const fl
  * (/root/reference/airfoilgcnn.py:94-143, airfoil_dqn.py:258-305).
  *   wsplit: mdq_qnet_staged_wsplit_floats() floats, filled by mdq_qnet_staged_wsplit() from the flat parameters and
  *           refreshed by the caller after every weight update (one launch);
- *   workspace: mdq_qnet_staged_workspace_floats() floats, 16-byte aligned, one per concurrent stream.
+ *   workspace: mdq_qnet_staged_workspace_floats() floats, 16-byte aligned, one per concurrent stream;
+ *   edge_src / edge_dst: the two rows of edge_index as int64 (PyG) or, with edge_i32 != 0, as int32 (the replay
+ *           minibatch travels over PCIe with 32-bit edges).
  * ------------------------------------------------------------------------------------ */
 int mdq_qnet_staged_supported(const mdq_net_t *net, int max_n, int max_e);
 int64_t mdq_qnet_staged_wsplit_floats(const mdq_net_t *net);
 int mdq_qnet_staged_wsplit(const mdq_net_t *net, const float *params, float *wsplit, void *stream);
 int64_t mdq_qnet_staged_workspace_floats(const mdq_net_t *net, int n_graphs, int max_n, int max_e, int backward);
 int mdq_qnet_staged_forward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
-                            const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                            const void *edge_src, const void *edge_dst, int edge_i32, const int32_t *node_ptr,
                             const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, float *out, float *embedding,
                             int32_t *argmax, float *workspace, void *stream);
 int mdq_qnet_staged_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
-                             const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                             const void *edge_src, const void *edge_dst, int edge_i32, const int32_t *node_ptr,
                              const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, const float *grad_out, float *grad,
                              float *workspace, void *stream);
 int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
-                                    const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                                    const void *edge_src, const void *edge_dst, int edge_i32, const int32_t *node_ptr,
                                     const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
                                     const int32_t *action, const float *reward, const int32_t *index,
                                     const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
@@ -200,6 +202,12 @@ int mdq_huber_replay(const float *q1, const float *q2, const int32_t *action, co
 int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
                   void *stream);
+
+/* Same update with the step count kept on the device (step_dev[0] = steps taken so far, incremented by the call): no
+ * host-computed bias corrections in the launch arguments, so a captured CUDA graph of the training step stays valid. */
+int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int32_t *step_dev,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Environment step, float64 geometry (replaces DOLFIN / shapely calls in

@@ -105,9 +105,9 @@ _SIGS = {
     "mdq_qnet_staged_wsplit_floats": (c_int64, [POINTER(mdq_net_t)]),
     "mdq_qnet_staged_wsplit": (c_int, [POINTER(mdq_net_t), _P, _P, _P]),
     "mdq_qnet_staged_workspace_floats": (c_int64, [POINTER(mdq_net_t), c_int, c_int, c_int, c_int]),
-    "mdq_qnet_staged_forward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
-    "mdq_qnet_staged_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
-    "mdq_qnet_staged_replay_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+    "mdq_qnet_staged_forward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "mdq_qnet_staged_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "mdq_qnet_staged_replay_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int,
                                                 _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, c_int, _P]),
     "mdq_qnet_layered_workspace_bytes": (c_int64, [POINTER(mdq_net_t), c_int, c_int]),
     "mdq_qnet_forward_layered": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),
@@ -117,6 +117,7 @@ _SIGS = {
     "mdq_node_gemm": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "mdq_huber_replay": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P]),
     "mdq_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
+    "mdq_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P, _P]),
     "mdq_scan_i32": (c_int, [_P, _P, c_int, _P]),
     "mdq_mesh_topology": (c_int, [_P, c_int, c_int] + [_P] * 14),
     "mdq_mesh_smooth": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
@@ -170,7 +171,7 @@ def check(rc: int, what: str = ""):
 
 def stream_ptr():
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def ptr(t):

@@ -34,6 +34,23 @@ else:  # the reference prints and falls back to CPU; here CPU tensors are only l
     device = torch.device("cpu")
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` only when `dev` is not already current (the context manager costs ~10 us of host time)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 class _Lin(nn.Module):
     def __init__(self, i, o, bias=True):
         super().__init__()
@@ -284,12 +301,23 @@ class _FusedQNet(nn.Module):
         x = data.x
         if not x.is_cuda:
             raise RuntimeError("meshdqn_b200 has no CPU path: move the data to a CUDA device (data.to('cuda'))")
-        x = x.float().contiguous()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
         ei = data.edge_index
-        if ei.dtype != torch.int64 or not ei.is_contiguous():
+        if ei.dtype == torch.int32 and ei.is_contiguous():
+            pass        # 32-bit edges (ReplayBatch arenas): read as they are by the staged kernels, widened for the others
+        elif ei.dtype != torch.int64 or not ei.is_contiguous():
             ei = ei.to(torch.int64).contiguous()
         nptr, eptr, B, max_n, max_e = graph_ptrs(data)
         return x, ei, nptr, eptr, B, max_n, max_e
+
+    @staticmethod
+    def _edge_ptrs(ei):
+        """(row 0 pointer, row 1 pointer, is_int32) of a contiguous [2, E] edge_index."""
+        E = int(ei.shape[1])
+        i32 = ei.dtype == torch.int32
+        base = ei.data_ptr()
+        return _lib.c_void_p(base), _lib.c_void_p(base + (4 if i32 else 8) * E), 1 if i32 else 0
 
     # -- staged tensor-core path (csrc/gnn_staged.cuh): tcgen05 3xTF32 GEMMs per stage instead of one CTA per graph ----
     qpath = os.environ.get("MDQ_QPATH", "auto")     # "auto": staged when the net / graph sizes allow it | "fused" | "staged"
@@ -297,7 +325,11 @@ class _FusedQNet(nn.Module):
     def _use_staged(self, max_n, max_e):
         if self.qpath == "fused":
             return False
-        ok = bool(_lib.lib().mdq_qnet_staged_supported(self._net, int(max_n), int(max_e)))
+        cache = self.__dict__.setdefault("_stg_ok", {})
+        key = (int(max_n), int(max_e), id(self._net))
+        ok = cache.get(key)
+        if ok is None:
+            ok = cache[key] = bool(_lib.lib().mdq_qnet_staged_supported(self._net, int(max_n), int(max_e)))
         if not ok and self.qpath == "staged":
             raise RuntimeError("qpath='staged': this network / graph size is not served by the staged kernels")
         return ok
@@ -311,21 +343,30 @@ class _FusedQNet(nn.Module):
             n = int(L.mdq_qnet_staged_wsplit_floats(self._net))
             if getattr(self, "_stg_w", None) is None or self._stg_w.numel() != n or self._stg_w.device != self._flat.device:
                 self._stg_w = torch.empty(n, dtype=torch.float32, device=self._flat.device)
-            with torch.cuda.device(self._flat.device):
+            with _on_device(self._flat.device):
                 rc = L.mdq_qnet_staged_wsplit(self._net, _lib.ptr(self._flat), _lib.ptr(self._stg_w), _lib.stream_ptr())
             _lib.check(rc, "mdq_qnet_staged_wsplit")
             self._stg_wver = ver
         return self._stg_w
 
+    def _staged_refresh(self):
+        """Bring the staged path's derived weights up to date now (no-op when they are, or when the net never ran staged)."""
+        if getattr(self, "_stg_w", None) is not None and getattr(self, "_flat", None) is not None:
+            self._staged_wsplit()
+
     def _staged_ws(self, B, max_n, max_e, backward, dev, shared=False):
         """Workspace of the staged launches, one per (stream, direction): replicas share a net across streams.
         ``shared``: one workspace whatever the stream (the two phases of the replay backward run on two streams)."""
-        need = int(_lib.lib().mdq_qnet_staged_workspace_floats(self._net, B, max_n, max_e, 1 if backward else 0))
+        sizes = self.__dict__.setdefault("_stg_need", {})
+        skey = (B, max_n, max_e, bool(backward))
+        need = sizes.get(skey)
+        if need is None:
+            need = sizes[skey] = int(_lib.lib().mdq_qnet_staged_workspace_floats(self._net, B, max_n, max_e, 1 if backward else 0))
         if need < 0:
             raise RuntimeError("mdq_qnet_staged_workspace_floats failed")
         if getattr(self, "_stg_wss", None) is None:
             self._stg_wss = {}
-        key = (0 if shared else torch.cuda.current_stream(dev).cuda_stream, bool(backward), dev.index)
+        key = (0 if shared else torch._C._cuda_getCurrentRawStream(dev.index), bool(backward), dev.index)
         ws = self._stg_wss.get(key)
         if ws is None or ws.numel() < need:
             ws = self._stg_wss[key] = torch.empty(need, dtype=torch.float32, device=dev)
@@ -348,13 +389,15 @@ class _FusedQNet(nn.Module):
         if self._use_staged(max_n, max_e):
             wsp = self._staged_wsplit()
             ws = self._staged_ws(B, max_n, max_e, False, x.device)
-            with torch.cuda.device(x.device):
-                rc = L.mdq_qnet_staged_forward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
-                                               _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+            e0, e1, i32 = self._edge_ptrs(ei)
+            with _on_device(x.device):
+                rc = L.mdq_qnet_staged_forward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x), e0, e1, i32,
                                                _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e, _lib.ptr(out),
                                                _lib.ptr(emb), _lib.ptr(am), _lib.ptr(ws), _lib.stream_ptr())
             _lib.check(rc, "mdq_qnet_staged_forward")
             return out, emb, am
+        if ei.dtype != torch.int64:
+            ei = ei.long()
         with torch.cuda.device(x.device):
             rc = L.mdq_qnet_forward(net, _lib.ptr(self._flat), _lib.ptr(x), _lib.c_void_p(ei.data_ptr()),
                                     _lib.c_void_p(ei.data_ptr() + 8 * E), _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e,
@@ -370,14 +413,15 @@ class _FusedQNet(nn.Module):
         if self._use_staged(max_n, max_e):
             wsp = self._staged_wsplit()
             ws = self._staged_ws(B, max_n, max_e, True, x.device)
-            E = int(ei.shape[1])
-            with torch.cuda.device(x.device):
-                rc = L.mdq_qnet_staged_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
-                                                _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+            e0, e1, i32 = self._edge_ptrs(ei)
+            with _on_device(x.device):
+                rc = L.mdq_qnet_staged_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x), e0, e1, i32,
                                                 _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e, _lib.ptr(gout),
                                                 _lib.ptr(flat_grad), _lib.ptr(ws), _lib.stream_ptr())
             _lib.check(rc, "mdq_qnet_staged_backward")
             return
+        if ei.dtype != torch.int64:
+            ei = ei.long()
         need = int(L.mdq_qnet_bwd_workspace_floats(net, B, max_n))
         if need < 0:
             raise RuntimeError("mdq_qnet_bwd_workspace_floats failed")
@@ -399,10 +443,9 @@ class _FusedQNet(nn.Module):
         if self._use_staged(max_n, max_e):
             wsp = self._staged_wsplit()
             ws = self._staged_ws(B, max_n, max_e, True, x.device, shared=True)
-            E = int(ei.shape[1])
-            with torch.cuda.device(x.device):
-                rc = L.mdq_qnet_staged_replay_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x),
-                                                       _lib.c_void_p(ei.data_ptr()), _lib.c_void_p(ei.data_ptr() + 8 * E),
+            e0, e1, i32 = self._edge_ptrs(ei)
+            with _on_device(x.device):
+                rc = L.mdq_qnet_staged_replay_backward(net, _lib.ptr(self._flat), _lib.ptr(wsp), _lib.ptr(x), e0, e1, i32,
                                                        _lib.ptr(nptr), _lib.ptr(eptr), B, max_n, max_e, int(mode),
                                                        _lib.ptr(action), _lib.ptr(reward), _lib.ptr(index),
                                                        _lib.ptr(next_slot), _lib.ptr(q_other), int(batch), float(gamma),
@@ -412,6 +455,8 @@ class _FusedQNet(nn.Module):
             return
         if phase == 1:
             return      # the fused kernel has no split: everything happens in the finishing call
+        if ei.dtype != torch.int64:
+            ei = ei.long()
 
         need = int(L.mdq_qnet_bwd_workspace_floats(net, B, max_n))
         if need < 0:
@@ -466,6 +511,8 @@ class _FusedQNet(nn.Module):
 
     def _launch_forward_layered(self, x, ei, embedding, want_argmax):
         self._ensure_packed()
+        if ei.dtype != torch.int64:
+            ei = ei.long()
         net = self._net
         net.x_stride = int(x.shape[1])
         N, E = int(x.shape[0]), int(ei.shape[1])

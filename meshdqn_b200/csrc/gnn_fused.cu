@@ -14,6 +14,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+
 #include "mdq_common.cuh"
 #include "tc_prims.cuh"
 
@@ -1750,6 +1754,36 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     }
 }
 
+// Adam with the step count on the device (CUDA-graph friendly: no host-computed bias corrections in the arguments).
+// step_dev[0] = steps taken so far; this launch is step t = step_dev[0] + 1; k_step_inc bumps the counter afterwards.
+__global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                                float gscale, const int *__restrict__ step_dev)
+{
+    __shared__ float sh[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)(step_dev[0] + 1);
+        const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+        sh[0] = (float)((double)lr / bc1);
+        sh[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = sh[0], bc2_sqrt = sh[1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        const float pi = p[i];
+        gi = fmaf(wd, pi, gi);
+        const float m0 = m[i];
+        const float mi = fmaf(gi - m0, 1.f - b1, m0);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+__global__ void k_step_inc(int *step_dev) { step_dev[0] += 1; }
+
 int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck, void (*kern)(const QArgs))
 {
     int rc = build_layout(*net, max_n, max_e, G, bwd, L, ck);
@@ -1976,6 +2010,25 @@ int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_a
     adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                               weight_decay, grad_scale, (float)((double)lr / bc1d), (float)sqrt(bc2d));
     return mdq::check_launch("adam_kernel");
+}
+
+int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int32_t *step_dev,
+                      void *stream)
+{
+    if (!params || !grad || !exp_avg || !exp_avg_sq || !step_dev || n < 1) {
+        mdq::set_error("mdq_adam_step_dev: bad argument");
+        return MDQ_EINVAL;
+    }
+    const int threads = 256;
+    int blocks = (int)((n + threads - 1) / threads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_dev_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                  weight_decay, grad_scale, step_dev);
+    int rc = mdq::check_launch("adam_dev_kernel");
+    if (rc != MDQ_OK) return rc;
+    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    return mdq::check_launch("k_step_inc");
 }
 
 }  // extern "C"

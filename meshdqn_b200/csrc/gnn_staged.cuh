@@ -210,7 +210,8 @@ struct S0Args {
     int x_stride, col0, b_off, pool_off;
     float ratio;
     const float *x;
-    const long long *esrc, *edst;
+    const long long *esrc, *edst;  // int64 edge_index rows, or int32 rows when edge_i32 (half the bytes over PCIe)
+    int edge_i32;
     const int *nptr, *eptr;
     int B, R1, EC1;
     float *x1;                     // [B][R1][128] kept rows x score
@@ -292,7 +293,14 @@ __global__ void __launch_bounds__(NTH, 2) k_stage0(const __grid_constant__ S0Arg
     __syncthreads();   // cursor zeroed: the edge loop below counts into it while the x rows are still in flight
     if (tid < 128) { bias[tid] = __ldg(a.params + a.b_off + tid); pw[tid] = __ldg(a.params + a.pool_off + tid); }
     for (int e = tid; e < E; e += NTH) {
-        const int s = (int)(a.esrc[eb0 + e] - nb0), d = (int)(a.edst[eb0 + e] - nb0);
+        int s, d;
+        if (a.edge_i32) {
+            s = reinterpret_cast<const int *>(a.esrc)[eb0 + e] - nb0;
+            d = reinterpret_cast<const int *>(a.edst)[eb0 + e] - nb0;
+        } else {
+            s = (int)(a.esrc[eb0 + e] - nb0);
+            d = (int)(a.edst[eb0 + e] - nb0);
+        }
         es[e] = (unsigned char)s;
         ed[e] = (unsigned char)d;
         atomicAdd(&cursor[d], 1);

@@ -77,17 +77,31 @@ int stg_smem_attr(K kern, int bytes, const char *name)
         mdq::set_error("%s: %d bytes of shared memory per CTA (> 227 KB)", name, bytes);
         return MDQ_ESMEM;
     }
+    // remembered per kernel (function address): the attribute calls cost ~10 us of host time each, 13 launches per step
+    static std::mutex mu;
+    static std::map<const void *, int> done;
+    const void *key = reinterpret_cast<const void *>(kern);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done.find(key);
+        if (it != done.end() && it->second >= bytes) return MDQ_OK;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { mdq::set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e)); return MDQ_ECUDA; }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        done[key] = bytes;
+    }
     return MDQ_OK;
 }
 
 struct StgCall {
     const mdq_net_t *net;
     const float *params, *wsplit, *x;
-    const int64_t *esrc, *edst;
+    const void *esrc, *edst;      // int64 (PyG edge_index rows) or int32 when edge_i32
+    int edge_i32;
     const int32_t *nptr, *eptr;
     float *out, *emb;
     int32_t *amax;
@@ -109,7 +123,8 @@ int stg_launch_01(const StgCall &c, const StgGeom &G, const stg::Plan &P, const 
         a.F = P.F; a.Fp = P.Fp; a.nch = P.k1pad / 4;
         a.x_stride = net.x_stride; a.col0 = net.in_col0; a.b_off = net.blk[0].b_off; a.pool_off = net.blk[0].pool_off;
         a.ratio = net.ratio;
-        a.x = c.x; a.esrc = (const long long *)c.esrc; a.edst = (const long long *)c.edst; a.nptr = c.nptr; a.eptr = c.eptr;
+        a.x = c.x; a.esrc = (const long long *)c.esrc; a.edst = (const long long *)c.edst; a.edge_i32 = c.edge_i32;
+        a.nptr = c.nptr; a.eptr = c.eptr;
         a.B = G.B; a.R1 = G.R1; a.EC1 = G.EC;
         a.x1 = w.x1; a.e1 = w.e1; a.e1n = w.e1n; a.r0 = w.r0;
         a.h1k = w.h1k; a.c1k = c1k; a.s1k = w.s1k; a.z1k = w.z1k; a.amax1 = w.amax1;
@@ -314,7 +329,7 @@ int64_t mdq_qnet_staged_workspace_floats(const mdq_net_t *net, int n_graphs, int
 }
 
 int mdq_qnet_staged_forward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
-                            const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                            const void *edge_src, const void *edge_dst, int edge_i32, const int32_t *node_ptr,
                             const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, float *out, float *embedding,
                             int32_t *argmax, float *workspace, void *stream)
 {
@@ -334,7 +349,7 @@ int mdq_qnet_staged_forward(const mdq_net_t *net, const float *params, const flo
     stg_geom(*net, n_graphs, max_n, max_e, G);
     StgWs w;
     stg_carve(G, workspace, false, w);
-    StgCall c{net, params, wsplit, x, edge_src, edge_dst, node_ptr, edge_ptr, out, embedding, argmax};
+    StgCall c{net, params, wsplit, x, edge_src, edge_dst, edge_i32, node_ptr, edge_ptr, out, embedding, argmax};
     int rc = stg_launch_01<false>(c, G, P, w, nullptr, nullptr, w.x2, st);
     if (rc != MDQ_OK) return rc;
     stg::TArgs a2;
@@ -343,7 +358,7 @@ int mdq_qnet_staged_forward(const mdq_net_t *net, const float *params, const flo
 }
 
 int mdq_qnet_staged_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
-                             const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                             const void *edge_src, const void *edge_dst, int edge_i32, const int32_t *node_ptr,
                              const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, const float *grad_out, float *grad,
                              float *workspace, void *stream)
 {
@@ -352,7 +367,7 @@ int mdq_qnet_staged_backward(const mdq_net_t *net, const float *params, const fl
         mdq::set_error("mdq_qnet_staged_backward: null / misaligned argument or empty batch");
         return MDQ_EINVAL;
     }
-    StgCall c{net, params, wsplit, x, edge_src, edge_dst, node_ptr, edge_ptr, nullptr, nullptr, nullptr};
+    StgCall c{net, params, wsplit, x, edge_src, edge_dst, edge_i32, node_ptr, edge_ptr, nullptr, nullptr, nullptr};
     stg::TArgs a2;
     memset(&a2, 0, sizeof(a2));
     a2.mode = 0; a2.gout = grad_out;
@@ -360,7 +375,7 @@ int mdq_qnet_staged_backward(const mdq_net_t *net, const float *params, const fl
 }
 
 int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, const float *wsplit, const float *x,
-                                    const int64_t *edge_src, const int64_t *edge_dst, const int32_t *node_ptr,
+                                    const void *edge_src, const void *edge_dst, int edge_i32, const int32_t *node_ptr,
                                     const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
                                     const int32_t *action, const float *reward, const int32_t *index,
                                     const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
@@ -372,7 +387,7 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
         mdq::set_error("mdq_qnet_staged_replay_backward: bad argument");
         return MDQ_EINVAL;
     }
-    StgCall c{net, params, wsplit, x, edge_src, edge_dst, node_ptr, edge_ptr, nullptr, nullptr, nullptr};
+    StgCall c{net, params, wsplit, x, edge_src, edge_dst, edge_i32, node_ptr, edge_ptr, nullptr, nullptr, nullptr};
     stg::TArgs a2;
     memset(&a2, 0, sizeof(a2));
     a2.mode = mode; a2.rp_action = action; a2.rp_reward = reward; a2.rp_index = index; a2.rp_qother = q_other;

@@ -67,7 +67,7 @@ class ReplayBatch:
     _arena = None      # uint8 tensor holding every tensor of the batch (pinned host, or its device copy)
     _layout = None     # [(slot, offset, dtype, shape)], slot = ("states", "x") / ("", "actions") / ...
 
-    def _named_tensors(self):
+    def _named_tensors(self, slim=False):
         out = [(("", k), getattr(self, k)) for k in ("actions", "next_slot", "rewards", "owner")]
         for name in ("states", "next_states"):
             b = getattr(self, name)
@@ -76,7 +76,10 @@ class ReplayBatch:
             m = b._host_meta()
             if m is None:
                 raise RuntimeError("ReplayBatch.pin_memory: collate on the host first (Batch.from_data_list)")
-            out += [((name, k), getattr(b, k)) for k in ("x", "edge_index", "batch", "ptr", "eptr")]
+            if slim:     # what the kernels read: features, 32-bit edges, 32-bit graph offsets
+                out += [((name, "x"), b.x), ((name, "edge_index"), b.edge_index.to(torch.int32))]
+            else:
+                out += [((name, k), getattr(b, k)) for k in ("x", "edge_index", "batch", "ptr", "eptr")]
             out += [((name, "_ptr32"), m[0]), ((name, "_eptr32"), m[1])]
         return out
 
@@ -98,7 +101,7 @@ class ReplayBatch:
                 continue
             d = parts[name]
             b = Batch(x=d["x"], edge_index=d["edge_index"])
-            b.batch, b.ptr, b.eptr, b.num_graphs = d["batch"], d["ptr"], d["eptr"], src.num_graphs
+            b.batch, b.ptr, b.eptr, b.num_graphs = d.get("batch"), d.get("ptr"), d.get("eptr"), src.num_graphs
             m = src._host_meta() or src.__dict__["_meta"]
             if arena.is_cuda:
                 b.__dict__["_mdq_ptrs"] = (d["_ptr32"], d["_eptr32"], m[2], m[3], m[4])
@@ -109,10 +112,12 @@ class ReplayBatch:
         out._arena, out._layout = arena, self._layout
         return out
 
-    def pin_memory(self):
+    def pin_memory(self, slim=False):
         """Pack every tensor of the minibatch into one pinned host arena (256-byte aligned sections): `to(device)` is
-        then a single cudaMemcpyAsync instead of ~18 small ones, which is what the host side of the e2e loop costs."""
-        named = self._named_tensors()
+        then a single cudaMemcpyAsync instead of ~18 small ones, which is what the host side of the e2e loop costs.
+        ``slim``: only what the kernels read travels -- ``edge_index`` as int32 and no ``batch`` / int64 offset
+        vectors (-25 % bytes over PCIe); the device batch then has ``batch = ptr = eptr = None`` and 32-bit edges."""
+        named = self._named_tensors(slim)
         layout, off = [], 0
         for slot, t in named:
             layout.append((slot, off, t.dtype, tuple(t.shape)))
@@ -162,26 +167,62 @@ class DevicePrefetcher:
     current stream wait for them and hands the device batch over; with a ~10 MB batch the PCIe copy of step k+1
     overlaps the kernels of step k instead of preceding them."""
 
-    def __init__(self, device):
+    def __init__(self, device, static=False):
+        """``static``: the copies land in two persistent device arenas used alternately, so consecutive minibatches of
+        the same layout come back at (two) fixed addresses -- what a captured CUDA graph of the training step needs
+        (``ReplayTrainer(graphs=True)``) -- and nothing is allocated per step."""
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
         self._pending = None
+        self.static = bool(static)
+        self._slots = []          # static mode: [device arena, ReplayBatch view, "consumer done" event]
+        self._turn = 0
 
     def submit(self, host_batch: "ReplayBatch"):
+        if self.static:
+            if host_batch._arena is None:
+                raise RuntimeError("DevicePrefetcher(static=True) needs an arena batch (ReplayBatch.pin_memory())")
+            if len(self._slots) < 2:
+                arena = torch.empty_like(host_batch._arena, device=self.device)
+                self._slots.append([arena, host_batch._from_arena(arena), None])
+            slot = self._slots[self._turn % 2]
+            self._turn += 1
+            if slot[0].numel() != host_batch._arena.numel() or slot[1]._layout is not host_batch._layout:
+                raise RuntimeError("static prefetcher: minibatch layout changed (use DevicePrefetcher(static=False))")
+            with torch.cuda.stream(self.stream):
+                if slot[2] is not None:
+                    self.stream.wait_event(slot[2])      # the step that read this arena two turns ago has finished
+                slot[0].copy_(host_batch._arena, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self._pending = (slot[1], ev, slot)
+            return
         with torch.cuda.stream(self.stream):
             dev = host_batch.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self._pending = (dev, ev)
+        self._pending = (dev, ev, None)
 
     def take(self) -> "ReplayBatch":
-        dev, ev = self._pending
+        dev, ev, slot = self._pending
         self._pending = None
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
-        for t in dev.tensors():          # allocated on the side stream, consumed on the current one
-            t.record_stream(cur)
+        if slot is None:
+            for t in dev.tensors():          # allocated on the side stream, consumed on the current one
+                t.record_stream(cur)
+        else:
+            self._last = slot
         return dev
+
+    def release(self):
+        """Static mode: call after the step that consumed the batch from ``take()`` has been enqueued."""
+        slot = getattr(self, "_last", None)
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            slot[2] = ev
+            self._last = None
 
 
 def multistep_lr(base_lr, step, milestones=(500000, 1000000, 1500000), gamma=0.1):
@@ -189,9 +230,35 @@ def multistep_lr(base_lr, step, milestones=(500000, 1000000, 1500000), gamma=0.1
     return base_lr * gamma ** sum(1 for m in milestones if step >= m)
 
 
+class _NoTimer:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_TIMER = _NoTimer()
+
+
+class _Timed:
+    def __init__(self, tr, name):
+        self.tr, self.name = tr, name
+
+    def __enter__(self):
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def __exit__(self, *a):
+        self.e1.record()
+        self.tr.timers.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
 class ReplayTrainer:
     def __init__(self, policy_net_1, policy_net_2, lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50,
-                 betas=(0.9, 0.999), eps=1e-8, process_group=None):
+                 betas=(0.9, 0.999), eps=1e-8, process_group=None, graphs=False):
         self.nets = (policy_net_1, policy_net_2)
         self.lr, self.wd, self.gamma = float(lr), float(weight_decay), float(gamma)
         self.betas, self.eps = betas, float(eps)
@@ -206,6 +273,11 @@ class ReplayTrainer:
         self.timers = None  # optional {name: [(start_event, end_event), ...]} for per-kernel timing
         self.overlap = True  # selected net's first stages on a side stream beside the other net's forward
         self._side = None
+        # graphs=True: the launches of a step (everything but the NCCL all-reduce) are captured once per (select branch,
+        # minibatch buffers) and replayed -- the ~13 launches cost ~200 us of host time per step otherwise, more than
+        # the kernels.  Needs minibatches at fixed device addresses (the same ReplayBatch, or DevicePrefetcher(static=True)).
+        self.graphs = bool(graphs)
+        self._graphs = {}
 
     # -- helpers ----------------------------------------------------------------------------
     def _adam_state(self, i):
@@ -213,30 +285,75 @@ class ReplayTrainer:
             net = self.nets[i]
             net._ensure_packed()
             z = torch.zeros_like(net._flat)
-            self._state[i] = dict(m=z, v=z.clone(), g=torch.zeros_like(net._flat), step=0)
+            self._state[i] = dict(m=z, v=z.clone(), g=torch.zeros_like(net._flat), step=0,
+                                  step_dev=torch.zeros(1, dtype=torch.int32, device=net._flat.device))
         return self._state[i]
 
     def _timed(self, name):
-        tr = self
-
-        class _T:
-            def __enter__(self_inner):
-                if tr.timers is not None:
-                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
-                    self_inner.e1 = torch.cuda.Event(enable_timing=True)
-                    self_inner.e0.record()
-
-            def __exit__(self_inner, *a):
-                if tr.timers is not None:
-                    self_inner.e1.record()
-                    tr.timers.setdefault(name, []).append((self_inner.e0, self_inner.e1))
-
-        return _T()
+        return _Timed(self, name) if self.timers is not None else _NO_TIMER
 
     # -- one replay step ----------------------------------------------------------------------
     @torch.no_grad()
     def step(self, batch: ReplayBatch, fused: bool = True):
         """Returns the Huber loss (device scalar tensor); parameters of the selected net are updated.
+        With ``graphs=True`` the step's launches are replayed from a captured CUDA graph (see ``__init__``)."""
+        if self.graphs and fused and self.timers is None:
+            return self._step_graph(batch)
+        return self._step_eager(batch, fused)
+
+    def _graph_key(self, batch):
+        t = [batch.states.x, batch.states.edge_index, batch.actions, batch.rewards, batch.next_slot, batch.owner]
+        if batch.next_states is not None:
+            t += [batch.next_states.x, batch.next_states.edge_index]
+        return (self.select, multistep_lr(self.lr, self.num_grads)) + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
+
+    def _step_graph(self, batch):
+        """Replay (or capture) the CUDA graph of one step on these minibatch buffers.  Host-side state that the kernels
+        bake into their arguments is kept out of the graph: Adam's step count lives on the device
+        (mdq_adam_step_dev), the learning rate and the select branch are part of the key."""
+        key = self._graph_key(batch)
+        sel = 0 if self.select else 1
+        net, other = self.nets[sel], self.nets[1 - sel]
+        entry = self._graphs.get(key)
+        if entry is None:
+            dev = batch.states.x.device
+            if len(self._graphs) >= 16:
+                self._graphs.pop(next(iter(self._graphs)))
+            # eager warm-up on a side stream (allocations, attribute set-up), on copies of nothing: one real step
+            loss = self._step_eager(batch, True, device_step=True, defer_bookkeeping=False)
+            if self._graph_key(batch) != key:     # that step flipped the select branch / crossed an lr milestone:
+                return loss                       # the branch it leads into is captured when it is first needed
+            sel = 0 if self.select else 1
+            net, other = self.nets[sel], self.nets[1 - sel]
+            torch.cuda.current_stream(dev).synchronize()
+            # the captured region refreshes the selected net's derived weights first, whatever the host thinks of them
+            g = torch.cuda.CUDAGraph()
+            state = (self.select, self.num_grads, self._state[sel]["step"])
+            other._staged_refresh()
+            net._stg_wver = None          # force the tile refresh of the selected net into the captured region
+            with torch.cuda.graph(g):
+                out = self._step_eager(batch, True, device_step=True, defer_bookkeeping=True, in_capture=True)
+            net._stg_wver = None          # ... which only recorded it: the tiles are still stale on the host's books
+            entry = self._graphs[key] = [g, out, batch]     # the batch is kept alive: the graph reads its buffers
+            # the capture pass only recorded work: nothing ran, host counters were not advanced (defer_bookkeeping)
+            assert state == (self.select, self.num_grads, self._state[sel]["step"])
+            return loss
+        other._staged_refresh()           # no-op unless the other net's weights changed since its tiles were built
+        entry[0].replay()
+        self._after_step(net, sel)
+        return entry[1]
+
+    def _after_step(self, net, sel):
+        net._bump_weights()               # raw-pointer write: derived weight copies (TF32 hi/lo tiles) are stale now
+        self._state[sel]["step"] += 1
+        self.num_grads += 1
+        if self.num_grads % self.target_update == 0:
+            self.select = not self.select
+
+    @torch.no_grad()
+    def _step_eager(self, batch: ReplayBatch, fused: bool = True, device_step: bool = False, defer_bookkeeping: bool = False,
+                    in_capture: bool = False):
+        """One step, launch by launch.
 
         fused=True (default): forward of the NON-selected net only; the selected net's backward kernel
         recomputes its own forward and evaluates the Huber term in place (mdq_qnet_replay_backward):
@@ -307,16 +424,16 @@ class ReplayTrainer:
         if self.world > 1:
             with self._timed("allreduce"):
                 torch.distributed.all_reduce(st["g"][:n_used], group=self.pg)
-        st["step"] += 1
         lr = multistep_lr(self.lr, self.num_grads)
-        with torch.cuda.device(dev), self._timed("adam"):
-            rc = L.mdq_adam_step(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0], self.betas[1],
-                                 self.eps, self.wd, 1.0 / self.world, st["step"], _lib.stream_ptr())
-        _lib.check(rc, "mdq_adam_step")
-        net._bump_weights()               # raw-pointer write: derived weight copies (TF32 hi/lo tiles) are stale now
-        self.num_grads += 1
-        if self.num_grads % self.target_update == 0:
-            self.select = not self.select
+        # the step count lives on the device (st["step_dev"], advanced by the call) so that the same launch arguments
+        # serve every step -- eager and graph-replayed steps share one Adam kernel and one counter
+        with self._timed("adam"):
+            rc = L.mdq_adam_step_dev(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0],
+                                     self.betas[1], self.eps, self.wd, 1.0 / self.world, p(st["step_dev"]),
+                                     _lib.stream_ptr())
+        _lib.check(rc, "mdq_adam_step_dev")
+        if not defer_bookkeeping:
+            self._after_step(net, sel)
         return loss
 
 

@@ -164,6 +164,7 @@ def test_layered_matches_fused_on_a_graph_both_can_run(cuda_device):
     from meshdqn_b200.data import Data
     g = torch.Generator().manual_seed(3)
     d = Data(x=torch.randn(180, 17, generator=g), edge_index=torch.randint(0, 180, (2, 369), generator=g)).to(cuda_device)
+    net.qpath = "fused"                       # this test is layered vs the fused single-launch kernel
     with torch.no_grad():
         q_fused = net(d).cpu()
         x, ei, *_ = net._prep(d)
