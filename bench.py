@@ -30,9 +30,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+# NOTE: the product arm imports nothing from oracle/ or tests/: its inputs come from meshdqn_b200.synthetic and the
+# fixture mesh files; only the `cpu_baseline` legs and `--impl reference` (below) execute the oracle.
 
 BATCH = 256
+STAGED_GROUP_TRAFFIC = None      # filled from profiles/r02_ncu_staged_replay.md once captured
 METRIC = "replay_train_graphs_per_s"
 UNIT = "graphs/s"
 
@@ -128,15 +130,27 @@ def random_transitions(n, seed):
             for i in range(n)]
 
 
+MESH_YS930 = os.path.join(ROOT, "tests", "golden", "mesh_ys930.npz")      # the reference's xdmf fixture, re-encoded
+
+
 def env_factory(device=None):
-    from conftest import make_config, oracle_fields
-    coords, cells, U, P = oracle_fields("ys930")
-    cfg = make_config()
-    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    """device given: the product environment, inputs built by the package itself.  device None: the CPU oracle
+    environment (cpu_baseline / --impl reference legs only), fields smoothed by the oracle's own smoother."""
+    from meshdqn_b200.synthetic import reference_config, synthetic_fields
+    cfg = reference_config()
     if device is None:
+        from oracle import geom
         from oracle.env_ref import Env2DAirfoilRef
+        z = np.load(MESH_YS930)
+        coords, cells = z["coords"].astype(np.float64), z["cells"].astype(np.int32)
+        topo = geom.Topology(cells, len(coords))
+        U, P = synthetic_fields(geom.smooth(coords, topo, 50), topo.edges, 5, 0)
+        cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
         return lambda: Env2DAirfoilRef(cfg, mesh=(coords, cells))
     from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
+    from meshdqn_b200.synthetic import fixture_environment_inputs
+    coords, cells, U, P = fixture_environment_inputs(MESH_YS930, device)
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
     return lambda: Env2DAirfoil(cfg, mesh=(coords, cells), device=device)
 
 
@@ -172,6 +186,63 @@ def cpu_replay_steps(transitions, max_seconds, max_steps, warmup):
         k += 1
     dt = time.perf_counter() - t0
     return k, dt
+
+
+def cpu_extras(transitions):
+    """cpu_baseline objects for the secondary metrics: the CPU oracle timed on this host
+    in the same run, bounded samples (~10 s in total).  GNN on all torch threads, geometry (scalar C) on one core."""
+    from meshdqn_b200.data import Batch
+    from oracle import geom, gnn_ref
+    torch.manual_seed(1370)
+    net = gnn_ref.NodeRemovalNet(181, 128, 0.1)
+    net.set_num_nodes(17)
+    states = [t[0] for t in transitions]
+    b256 = Batch.from_data_list(states)
+    out = {}
+
+    def timed(fn, budget, max_n, warm=1):
+        for _ in range(warm):
+            fn()
+        t0 = time.perf_counter()
+        n = 0
+        while n < max_n and time.perf_counter() - t0 < budget:
+            fn()
+            n += 1
+        return n, time.perf_counter() - t0
+    with torch.no_grad():
+        n, dt = timed(lambda: net(b256), 3.0, 100)
+        out["q_eval_b256"] = {"value": len(states) * n / dt, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+                              "sample": f"{n} forward passes of the same {len(states)}-graph batch, CPU oracle (torch fp32)"}
+        n, dt = timed(lambda: net(states[0]), 2.0, 2000)
+        out["q_eval_b1"] = {"value": n / dt, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"{n} single-graph forward passes, CPU oracle (torch fp32)"}
+    with quiet():
+        env = env_factory(None)()
+        rng = np.random.RandomState(0)
+        s = env.get_state()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 400 and time.perf_counter() - t0 < 4.0:
+            with torch.no_grad():
+                net(s)
+            s, r, done, _ = env.step(int(rng.randint(0, 180)))
+            n += 1
+            if done:
+                env = env_factory(None)()
+                s = env.get_state()
+        dt = time.perf_counter() - t0
+    out["env_step_ys930"] = {"value": n / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                             "sample": f"{n} steps (Q-eval + Qhull + smoothing + brute-force locate + P2 evaluation + drag/lift), CPU oracle"}
+    fs = env.flow_solver
+    pts = fs.topo.p2_points(fs.coords)
+
+    def reinterp():
+        cell_of, _, _ = geom.locate(pts, env.coords0, env.topo0.cells)
+        geom.eval_fields(pts, fs.num_vertices, cell_of, env.coords0, env.topo0, env.U0, env.P0)
+    n, dt = timed(reinterp, 2.0, 500)
+    out["reinterp_ys930"] = {"value": len(pts) * n / dt, "unit": "vertices/s", "cores": 1, "kind": "port",
+                             "sample": f"{n} re-interpolations of {len(pts)} dof points x 5 snapshots (brute-force locate), CPU oracle C"}
+    return out
 
 
 def run_reference(args):
@@ -216,7 +287,7 @@ def run_ours(args):
 
     tr = random_transitions(BATCH, 1000 + rank) if args.fast_setup else harvest_transitions(env_factory(dev), BATCH, 1000 + rank)
     rb_host = ReplayBatch.from_transitions(tr).pin_memory(slim=True)   # features + 32-bit edges + 32-bit offsets only
-    rb_dev = rb_host.to(dev)
+    rb_dev = rb_host.to(dev).mark_static()       # stepped K times in place: the trainer may capture the step on it
     torch.manual_seed(1370)
     nets = []
     for _ in range(2):
@@ -290,6 +361,29 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     e2e_val = world * BATCH * K / e2e_s
+
+    # ---- strong scaling (SURVEY.md 7 hard part 5): the SAME global minibatch of 256 graphs split over the
+    # ranks.  32 graphs per GPU at N = 8 are far below one wave of anything, so this is expected to stay well under 2x:
+    # every kernel of the step is latency-bound at that size and the all-reduce is a fixed ~20-40 us on top.
+    strong = None
+    if world > 1:
+        per = BATCH // world
+        rb_s = ReplayBatch.from_transitions(tr[:per]).pin_memory(slim=True).to(dev).mark_static()
+        for sel in (False, True):
+            trainer.select = sel
+            for _ in range(W + 2):
+                trainer.step(rb_s)
+        trainer.select = True
+        barrier()
+        evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for e0, e1 in evs2:
+            flush.fill_(1)
+            e0.record()
+            trainer.step(rb_s)
+            e1.record()
+        barrier()
+        ms_s = max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs2), dev) / K
+        strong = {"global_batch": per * world, "graphs_per_gpu": per, "ms_per_step": ms_s, "graphs_per_s": per * world / (ms_s * 1e-3)}
 
     # ---- the same loop fed from the DEVICE-resident replay memory -- sample (host-side index
     # draw + ~12 KB of offsets over PCIe + one gather launch) + step + lagged loss read-back; no minibatch H2D ----
@@ -370,14 +464,23 @@ def run_ours(args):
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rb_host.h2d_bytes()), "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "qnet_kernel<bwd> + wgrad_partial + wgrad_reduce", "achieved": achieved,
-                             "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm,
-                             # dram__bytes_read+write per launch of the group from one `ncu --set full` capture (cold caches):
-                             # qnet_kernel<bwd> 5.62 MB + wgrad_partial 6.20 MB + wgrad_reduce 8.00 MB (profiles/r01_ncu_raw_qnet_replay.txt)
-                             "traffic": 19822336,
+                "roofline": {"bound": "hbm",
+                             "kernel": "backward group of the selected net: k_stage0<save> + k_stage1<save> (tcgen05) + k_tail<bwd> + "
+                                       "k_bwd1 + wgrad_partial + wgrad_reduce",
+                             "achieved": achieved, "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm,
+                             # dram__bytes_read+write per launch, summed over the group, from one `ncu --set full` capture
+                             # (cold caches; profiles/r02_ncu_staged_replay.md)
+                             "traffic": STAGED_GROUP_TRAFFIC,
                              "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": dom_us,
-                             "note": "launch/latency-bound at 256 x 180-node graphs (15 KB per graph); see DESIGN.md"},
+                             "note": "latency-bound by construction at 256 x 180-node graphs (15 KB per graph, 0.5 MB of weights): "
+                                     "the fraction is reported as the contract asks, the per-kernel cycle traces in profiles/ are the "
+                                     "optimisation signal; see DESIGN.md 4.1"},
                 "kernel_us": kern, "extras": extras}
+        line["extras"]["strong_scaling"] = dict(
+            strong if strong is not None else {"global_batch": BATCH, "graphs_per_gpu": BATCH, "ms_per_step": ms_step,
+                                               "graphs_per_s": value},
+            note="same 256-graph global minibatch split over the ranks; expected < 2x at 8 GPUs (32 graphs per GPU: every "
+                 "kernel is latency-bound and the all-reduce is a fixed cost) -- the >= 6x target refers to weak scaling")
         line["extras"]["replay_device_memory"] = {
             "graphs_per_s": mem_val, "unit": UNIT, "host_resample_collate_graphs_per_s": host_val,
             "note": "same step, minibatch sampled from the device-resident replay memory (one gather launch, ~12 KB of "
@@ -387,6 +490,10 @@ def run_ours(args):
             k, dt = cpu_replay_steps(tr, max_seconds=15.0, max_steps=1000, warmup=1)
             line["cpu_baseline"] = {"value": BATCH * k / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{k} replay steps of the same {BATCH}-graph batch in {dt:.1f} s, CPU oracle (torch fp32)"}
+            if not args.no_extras:
+                for name, cb in cpu_extras(tr).items():
+                    if name in line["extras"]:
+                        line["extras"][name]["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -413,8 +520,9 @@ def bench_candidates(net, rb_dev, dev, rank, world, flush, total=8192):
     from meshdqn_b200.data import Batch
     from meshdqn_b200.parallel import max_over_ranks, shard_range
     import torch.distributed as dist
+    from meshdqn_b200.airfoilgcnn import graph_ptrs
     st = rb_dev.states
-    nb = int(st.ptr.numel()) - 1
+    nptr32, eptr32, nb, _, _ = graph_ptrs(st)
     lo, hi = shard_range(total, rank, world)
     nloc = hi - lo
     reps = (nloc + nb - 1) // nb
@@ -422,7 +530,7 @@ def bench_candidates(net, rb_dev, dev, rank, world, flush, total=8192):
     x = st.x.repeat(reps, 1)
     rr = torch.arange(reps, device=dev)
     ei = (st.edge_index.unsqueeze(0) + (rr * N).view(-1, 1, 1)).permute(1, 0, 2).reshape(2, -1).contiguous()
-    p0, e0 = st.ptr.to(dev).long(), st.eptr.to(dev).long()
+    p0, e0 = nptr32.long(), eptr32.long()
     ptr = torch.cat([(p0[:-1].unsqueeze(0) + (rr * N).view(-1, 1)).reshape(-1), torch.tensor([reps * N], device=dev)])
     eptr = torch.cat([(e0[:-1].unsqueeze(0) + (rr * E).view(-1, 1)).reshape(-1), torch.tensor([reps * E], device=dev)])
     b = Batch(x=x, edge_index=ei)
@@ -461,8 +569,10 @@ def measure_extras(dev, net, rb_dev, flush, args):
         ms = time_events(f, 20, flush)
         out["q_eval_b256"] = {"graphs_per_s": BATCH / (ms * 1e-3), "us_per_launch": ms * 1e3}
         from meshdqn_b200.data import Data
-        n0 = int(rb_dev.states.ptr[1])
-        e0 = int(rb_dev.states.eptr[1])
+        from meshdqn_b200.airfoilgcnn import graph_ptrs
+        nptr32, eptr32, *_ = graph_ptrs(rb_dev.states)
+        n0 = int(nptr32[1])
+        e0 = int(eptr32[1])
         one = Data(x=rb_dev.states.x[:n0].contiguous(), edge_index=rb_dev.states.edge_index[:, :e0].contiguous())
         oargs = net._prep(one)
         f1 = lambda: net._launch_forward(*oargs, False, True)

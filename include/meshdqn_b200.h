@@ -40,6 +40,9 @@ const char *mdq_last_error(void);
 int mdq_version(void);
 /* number of kernel launches issued through this library by the calling process */
 int64_t mdq_launch_count(void);
+/* a replayed CUDA graph launches the kernels recorded at capture time without passing through this library: the host
+ * mirror adds that number per replay so that mdq_launch_count() stays the number of kernel launches that ran */
+void mdq_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------------------------
  * Q-network (replaces torch_geometric SAGEConv/GCNConv/TopKPooling/global pools +

@@ -92,6 +92,7 @@ _SIGS = {
     "mdq_last_error": (ctypes.c_char_p, []),
     "mdq_version": (c_int, []),
     "mdq_launch_count": (c_int64, []),
+    "mdq_launch_count_add": (None, [c_int64]),
     "mdq_qnet_set_trace": (None, [_P]),
     "mdq_qnet_smem_bytes": (c_int64, [POINTER(mdq_net_t), c_int, c_int, c_int, c_int]),
     "mdq_qnet_occupancy": (c_int, [POINTER(mdq_net_t), c_int, c_int, c_int]),

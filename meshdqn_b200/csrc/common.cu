@@ -26,4 +26,5 @@ extern "C" {
 const char *mdq_last_error(void) { return mdq::g_err; }
 int mdq_version(void) { return 100; }
 int64_t mdq_launch_count(void) { return mdq::g_launches.load(std::memory_order_relaxed); }
+void mdq_launch_count_add(int64_t n) { mdq::g_launches.fetch_add(n, std::memory_order_relaxed); }
 }

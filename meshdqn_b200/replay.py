@@ -64,6 +64,8 @@ class ReplayBatch:
                    torch.tensor([float(r) for r in rewards], dtype=torch.float32))
 
     # -- host staging: ONE pinned arena, ONE host->device copy per minibatch ---------------------------
+    static = False     # True: these device buffers are refilled in place / reused step after step, so a ReplayTrainer with
+                       # graphs=True may capture its launches on them (set by mark_static / DevicePrefetcher(static=True))
     _arena = None      # uint8 tensor holding every tensor of the batch (pinned host, or its device copy)
     _layout = None     # [(slot, offset, dtype, shape)], slot = ("states", "x") / ("", "actions") / ...
 
@@ -111,6 +113,11 @@ class ReplayBatch:
         out = ReplayBatch(batches["states"], p["actions"], batches["next_states"], p["next_slot"], p["rewards"], p["owner"])
         out._arena, out._layout = arena, self._layout
         return out
+
+    def mark_static(self):
+        """Promise that this device batch's buffers stay where they are and are only ever refilled in place."""
+        self.static = True
+        return self
 
     def pin_memory(self, slim=False):
         """Pack every tensor of the minibatch into one pinned host arena (256-byte aligned sections): `to(device)` is
@@ -184,7 +191,7 @@ class DevicePrefetcher:
                 raise RuntimeError("DevicePrefetcher(static=True) needs an arena batch (ReplayBatch.pin_memory())")
             if len(self._slots) < 2:
                 arena = torch.empty_like(host_batch._arena, device=self.device)
-                self._slots.append([arena, host_batch._from_arena(arena), None])
+                self._slots.append([arena, host_batch._from_arena(arena).mark_static(), None])
             slot = self._slots[self._turn % 2]
             self._turn += 1
             if slot[0].numel() != host_batch._arena.numel() or slot[1]._layout is not host_batch._layout:
@@ -278,6 +285,7 @@ class ReplayTrainer:
         # the kernels.  Needs minibatches at fixed device addresses (the same ReplayBatch, or DevicePrefetcher(static=True)).
         self.graphs = bool(graphs)
         self._graphs = {}
+        self._seen = set()
 
     # -- helpers ----------------------------------------------------------------------------
     def _adam_state(self, i):
@@ -297,14 +305,15 @@ class ReplayTrainer:
     def step(self, batch: ReplayBatch, fused: bool = True):
         """Returns the Huber loss (device scalar tensor); parameters of the selected net are updated.
         With ``graphs=True`` the step's launches are replayed from a captured CUDA graph (see ``__init__``)."""
-        if self.graphs and fused and self.timers is None:
+        if self.graphs and fused and self.timers is None and getattr(batch, "static", False):
             return self._step_graph(batch)
         return self._step_eager(batch, fused)
 
     def _graph_key(self, batch):
         t = [batch.states.x, batch.states.edge_index, batch.actions, batch.rewards, batch.next_slot, batch.owner]
+        t += list(graph_ptrs(batch.states)[:2])
         if batch.next_states is not None:
-            t += [batch.next_states.x, batch.next_states.edge_index]
+            t += [batch.next_states.x, batch.next_states.edge_index] + list(graph_ptrs(batch.next_states)[:2])
         return (self.select, multistep_lr(self.lr, self.num_grads)) + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
 
     def _step_graph(self, batch):
@@ -316,6 +325,14 @@ class ReplayTrainer:
         net, other = self.nets[sel], self.nets[1 - sel]
         entry = self._graphs.get(key)
         if entry is None:
+            # only minibatches marked `static` get here (fixed device buffers that are refilled in place: the same
+            # ReplayBatch stepped repeatedly, DevicePrefetcher(static=True)); even so a key is captured the second time
+            # it shows up, so a buffer used once costs nothing extra
+            if key not in self._seen:
+                if len(self._seen) >= 64:
+                    self._seen.clear()
+                self._seen.add(key)
+                return self._step_eager(batch, True)
             dev = batch.states.x.device
             if len(self._graphs) >= 16:
                 self._graphs.pop(next(iter(self._graphs)))
@@ -328,18 +345,22 @@ class ReplayTrainer:
             torch.cuda.current_stream(dev).synchronize()
             # the captured region refreshes the selected net's derived weights first, whatever the host thinks of them
             g = torch.cuda.CUDAGraph()
+            n0 = int(_lib.lib().mdq_launch_count())
             state = (self.select, self.num_grads, self._state[sel]["step"])
             other._staged_refresh()
             net._stg_wver = None          # force the tile refresh of the selected net into the captured region
             with torch.cuda.graph(g):
                 out = self._step_eager(batch, True, device_step=True, defer_bookkeeping=True, in_capture=True)
             net._stg_wver = None          # ... which only recorded it: the tiles are still stale on the host's books
-            entry = self._graphs[key] = [g, out, batch]     # the batch is kept alive: the graph reads its buffers
+            n_launch = int(_lib.lib().mdq_launch_count()) - n0
+            _lib.lib().mdq_launch_count_add(-n_launch)      # recorded, not run
+            entry = self._graphs[key] = [g, out, batch, n_launch]   # the batch is kept alive: the graph reads its buffers
             # the capture pass only recorded work: nothing ran, host counters were not advanced (defer_bookkeeping)
             assert state == (self.select, self.num_grads, self._state[sel]["step"])
             return loss
         other._staged_refresh()           # no-op unless the other net's weights changed since its tiles were built
         entry[0].replay()
+        _lib.lib().mdq_launch_count_add(entry[3])
         self._after_step(net, sel)
         return entry[1]
 

@@ -189,3 +189,35 @@ def synthetic_airfoil_mesh(n_triangles=250_000, seed=0, n_airfoil=None, order="r
     cells = cells[is_b[cells].sum(1) != 3]
     cells = np.sort(cells, axis=1).astype(np.int32)
     return np.ascontiguousarray(coords), np.ascontiguousarray(cells), len(ring)
+
+
+def reference_config(N_closest=180, timesteps=10000, threshold=0.001, smooth=True, **extra):
+    """The reference's YAML (/root/reference/configs/ray_ys930.yaml:1-39) as a dict; mesh and fields are injected."""
+    cfg = {
+        "flow_config": {
+            "flow_params": {"mu": 1e-3, "rho": 1.0, "inflow": "constant"},
+            "geometry_params": {"mesh": None},
+            "solver_params": {"dt": 0.001, "solver_type": "lu", "smooth": smooth},
+        },
+        "agent_params": dict(solver_steps=5000, episodes=1000000, timesteps=timesteps, threshold=threshold,
+                             N_closest=N_closest, gt_drag=-1, gt_time=-1, u=-1, p=-1, do_nothing=True, time_reward=0.005,
+                             smoothing=True, save_steps=1000, goal_vertices=0.95, plot_dir=""),
+        "optimizer": {"lr": 1e-5, "weight_decay": 1e-6, "batch_size": 32},
+        "epsilon": {"decay": 10000, "start": 1.0, "end": 0.01, "gamma": 1.0},
+    }
+    cfg["agent_params"].update(extra)
+    return cfg
+
+
+def fixture_environment_inputs(mesh_npz, device, T=5, seed=0):
+    """(coords, cells, U, P) for an environment on a shipped fixture mesh: the mesh is smoothed on the DEVICE
+    (``DeviceMesh.smooth(50)``, the kernel the environment itself uses) and the analytic snapshots are sampled on the
+    smoothed dof points -- the product-side twin of the oracle-smoothed fields the tests build (same bits: the device
+    smoother is bit-identical to the oracle's)."""
+    from .flow_solver import DeviceMesh
+    z = np.load(mesh_npz)
+    coords, cells = z["coords"].astype(np.float64), z["cells"].astype(np.int32)
+    m = DeviceMesh(coords, cells, device)
+    m.smooth(50)
+    U, P = synthetic_fields(m.coordinates(), m.edges.cpu().numpy(), T, seed)
+    return coords, cells, U, P
