@@ -495,9 +495,17 @@ def run_ours(args):
                     if name in line["extras"]:
                         line["extras"][name]["cpu_baseline"] = cb
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # Captured CUDA graphs hold NCCL kernels of this communicator; tearing the process group down under them hung
+        # (round 2, N = 2).  Drop the graphs, drain the device, meet once more, then leave without running destructors.
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def time_events(fn, iters, flush=None):
