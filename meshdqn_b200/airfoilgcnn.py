@@ -349,10 +349,29 @@ class _FusedQNet(nn.Module):
             self._stg_wver = ver
         return self._stg_w
 
-    def _staged_refresh(self):
-        """Bring the staged path's derived weights up to date now (no-op when they are, or when the net never ran staged)."""
+    def _staged_refresh(self, force=False):
+        """Bring the staged path's derived weights up to date now (no-op when they are, or when the net never ran staged).
+        ``force``: launch the refresh whatever the host's bookkeeping says (inside a captured graph)."""
         if getattr(self, "_stg_w", None) is not None and getattr(self, "_flat", None) is not None:
+            if force:
+                self._stg_wver = None
             self._staged_wsplit()
+
+    def _staged_mark_fresh(self):
+        if getattr(self, "_stg_w", None) is not None:
+            self._stg_wver = self._weights_version()
+
+    def state_dict(self, *args, **kwargs):
+        flat = getattr(self, "_flat", None)
+        if flat is not None and flat.is_cuda:
+            self._wait_pending(flat.device)      # a trainer's update of these weights may still be in flight
+        return super().state_dict(*args, **kwargs)
+
+    def _wait_pending(self, dev):
+        """A trainer may still have this net's update in flight on its update stream (ReplayTrainer, segment U)."""
+        ev = self.__dict__.get("_pending")
+        if ev is not None:
+            torch.cuda.current_stream(dev).wait_event(ev)
 
     def _staged_ws(self, B, max_n, max_e, backward, dev, shared=False):
         """Workspace of the staged launches, one per (stream, direction): replicas share a net across streams.
@@ -551,6 +570,7 @@ class _FusedQNet(nn.Module):
     def _forward_impl(self, data, embedding=False):
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
         self._ensure_packed()
+        self._wait_pending(x.device)
         if self._use_layered(B, max_n, max_e):
             if torch.is_grad_enabled() and any(p.requires_grad for _, p in self._entries):
                 raise NotImplementedError("the layered large-graph path is forward-only (Q-evaluation); wrap the call in "
@@ -568,6 +588,7 @@ class _FusedQNet(nn.Module):
         """Fused softmax + argmax (airfoil_dqn.py:208-209): returns (action i32 [B], q [B, A])."""
         x, ei, nptr, eptr, B, max_n, max_e = self._prep(data)
         self._ensure_packed()
+        self._wait_pending(x.device)
         if self._use_layered(B, max_n, max_e):
             out, _, am = self._launch_forward_layered(x, ei, False, True)
             return am, out

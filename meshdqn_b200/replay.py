@@ -278,8 +278,9 @@ class ReplayTrainer:
         self.num_grads = 0
         self._state = [None, None]
         self.timers = None  # optional {name: [(start_event, end_event), ...]} for per-kernel timing
-        self.overlap = True  # selected net's first stages on a side stream beside the other net's forward
+        self.overlap = True  # segments on three streams (see "one replay step" below); False: everything on the current one
         self._side = None
+        self._upd = None
         # graphs=True: the launches of a step (everything but the NCCL all-reduce) are captured once per (select branch,
         # minibatch buffers) and replayed -- the ~13 launches cost ~200 us of host time per step otherwise, more than
         # the kernels.  Needs minibatches at fixed device addresses (the same ReplayBatch, or DevicePrefetcher(static=True)).
@@ -301,13 +302,157 @@ class ReplayTrainer:
         return _Timed(self, name) if self.timers is not None else _NO_TIMER
 
     # -- one replay step ----------------------------------------------------------------------
+    # -- one replay step ----------------------------------------------------------------------
+    #
+    # Segments of a (fused) step and the streams they run on:
+    #   H  selected net, stages 0 / 1 (do not read Q_other)             side stream   | beside A
+    #   A  forward of the other net -> Q_other                          main stream   |
+    #   T  selected net: tail backward, backward 1, weight gradients, loss           main stream, after H and A
+    #   U  [all-reduce] + Adam + refresh of the selected net's weight tiles           update stream, after T
+    # U of step k is NOT waited for by step k+1's A (the other net is not the one being updated), only by its H: the
+    # all-reduce and the optimizer run under the next step's forward.  Every net remembers the event of its last
+    # update (`_pending`); its launches wait for it, ReplayTrainer.flush() joins everything to the current stream.
+
+    def _streams(self, dev):
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+            self._upd = torch.cuda.Stream(dev)
+        return self._side, self._upd
+
+    def flush(self):
+        """Make the current stream wait for every enqueued update (call before reading weights with plain torch ops:
+        ``state_dict()``, checkpoints, comparisons)."""
+        for n in self.nets:
+            ev = n.__dict__.get("_pending")
+            if ev is not None:
+                torch.cuda.current_stream(n._flat.device).wait_event(ev)
+
+    def _roles(self, batch):
+        net1, net2 = self.nets
+        s_args = net1._prep(batch.states)
+        n_args = net2._prep(batch.next_states) if batch.next_states is not None else None
+        sel = 0 if self.select else 1
+        if self.select:
+            return sel, s_args, 1, batch.next_slot, net2, n_args
+        return sel, n_args, 2, batch.owner, net1, s_args
+
+    def _seg_H(self, batch, r, scalar, loss):
+        sel, args, mode, index, other, o_args = r
+        st = self._adam_state(sel)
+        self.nets[sel]._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, None,
+                                               int(batch.actions.shape[0]), self.gamma, scalar, loss, st["g"], phase=1)
+
+    def _seg_A(self, r):
+        other, o_args = r[4], r[5]
+        if o_args is None:
+            return None
+        return other._launch_forward(*o_args, False, False)[0]
+
+    def _seg_T(self, batch, r, q_other, scalar, loss, phase):
+        sel, args, mode, index, other, o_args = r
+        st = self._adam_state(sel)
+        self.nets[sel]._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, q_other,
+                                               int(batch.actions.shape[0]), self.gamma, scalar, loss, st["g"], phase=phase)
+
+    def _seg_U(self, sel, refresh=True):
+        net, st = self.nets[sel], self._adam_state(sel)
+        n_used = net._n_used
+        L, p = _lib.lib(), _lib.ptr
+        if self.world > 1:
+            with self._timed("allreduce"):
+                torch.distributed.all_reduce(st["g"][:n_used], group=self.pg)
+        lr = multistep_lr(self.lr, self.num_grads)
+        # the step count lives on the device (st["step_dev"], advanced by the call) so that the same launch arguments
+        # serve every step -- eager and graph-replayed steps share one Adam kernel and one counter
+        with self._timed("adam"):
+            rc = L.mdq_adam_step_dev(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0],
+                                     self.betas[1], self.eps, self.wd, 1.0 / self.world, p(st["step_dev"]),
+                                     _lib.stream_ptr())
+        _lib.check(rc, "mdq_adam_step_dev")
+        if refresh:
+            net._staged_refresh(force=True)      # the tiles follow the weights on the update stream, off the next step's path
+
+    def _after_step(self, net, sel, fresh):
+        net._bump_weights()               # raw-pointer write: derived weight copies (TF32 hi/lo tiles) are stale now ...
+        if fresh:
+            net._staged_mark_fresh()      # ... unless segment U rebuilt them right behind the optimizer
+        self._state[sel]["step"] += 1
+        self.num_grads += 1
+        if self.num_grads % self.target_update == 0:
+            self.select = not self.select
+
     @torch.no_grad()
     def step(self, batch: ReplayBatch, fused: bool = True):
-        """Returns the Huber loss (device scalar tensor); parameters of the selected net are updated.
-        With ``graphs=True`` the step's launches are replayed from a captured CUDA graph (see ``__init__``)."""
-        if self.graphs and fused and self.timers is None and getattr(batch, "static", False):
-            return self._step_graph(batch)
-        return self._step_eager(batch, fused)
+        """Returns the Huber loss (device scalar tensor); the selected net's update is enqueued (see ``flush``).
+
+        fused=True (default): forward of the NON-selected net only; the selected net's backward launches recompute its
+        own forward and evaluate the Huber term in place.  With ``graphs=True`` and a batch marked static the segments
+        are replayed from captured CUDA graphs.
+        fused=False: the reference's literal sequence forward(Q1), forward(Q2), Huber, backward (used by tests)."""
+        if not fused or self.timers is not None or not self.overlap:
+            return self._step_serial(batch, fused)
+        r = self._roles(batch)
+        sel, args, mode, index, other, o_args = r
+        if args is None:                    # every transition terminal and the next-state net selected: nothing to train on
+            return self._step_serial(batch, fused)
+        dev = batch.states.x.device
+        net = self.nets[sel]
+        main = torch.cuda.current_stream(dev)
+        side, upd = self._streams(dev)
+        use_graph = self.graphs and getattr(batch, "static", False)
+        entry = None
+        if use_graph:
+            key = self._graph_key(batch)
+            entry = self._graphs.get(key)
+            if entry is None:
+                if key in self._seen:
+                    entry = self._capture(batch, key, r)
+                else:
+                    if len(self._seen) >= 64:
+                        self._seen.clear()
+                    self._seen.add(key)
+        pend_net, pend_other = net.__dict__.get("_pending"), other.__dict__.get("_pending")
+        # H on the side stream: after the inputs (main) and the selected net's previous update
+        side.wait_stream(main)
+        if pend_net is not None:
+            side.wait_event(pend_net)
+        if entry is None:
+            scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(side):
+            if entry is not None:
+                entry["H"].replay()
+            else:
+                self._seg_H(batch, r, scalar, loss)
+        # A on the main stream: only a freshly de-selected net still has an update in flight
+        if pend_other is not None:
+            main.wait_event(pend_other)
+        if entry is not None:
+            entry["A"].replay()
+        else:
+            q_other = self._seg_A(r)
+        main.wait_stream(side)
+        if entry is not None:
+            entry["T"].replay()
+            loss = entry["loss"]
+        else:
+            self._seg_T(batch, r, q_other, scalar, loss, 2)
+        # U on the update stream
+        ev = torch.cuda.Event()
+        ev.record(main)
+        upd.wait_event(ev)
+        with torch.cuda.stream(upd):
+            if entry is not None:
+                entry["U"].replay()
+            else:
+                self._seg_U(sel)
+            done = torch.cuda.Event()
+            done.record(upd)
+        net._pending = done
+        if entry is not None:
+            _lib.lib().mdq_launch_count_add(entry["n"])
+        self._after_step(net, sel, fresh=True)
+        return loss
 
     def _graph_key(self, batch):
         t = [batch.states.x, batch.states.edge_index, batch.actions, batch.rewards, batch.next_slot, batch.owner]
@@ -316,112 +461,69 @@ class ReplayTrainer:
             t += [batch.next_states.x, batch.next_states.edge_index] + list(graph_ptrs(batch.next_states)[:2])
         return (self.select, multistep_lr(self.lr, self.num_grads)) + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
 
-    def _step_graph(self, batch):
-        """Replay (or capture) the CUDA graph of one step on these minibatch buffers.  Host-side state that the kernels
-        bake into their arguments is kept out of the graph: Adam's step count lives on the device
-        (mdq_adam_step_dev), the learning rate and the select branch are part of the key."""
-        key = self._graph_key(batch)
-        sel = 0 if self.select else 1
-        net, other = self.nets[sel], self.nets[1 - sel]
-        entry = self._graphs.get(key)
-        if entry is None:
-            # only minibatches marked `static` get here (fixed device buffers that are refilled in place: the same
-            # ReplayBatch stepped repeatedly, DevicePrefetcher(static=True)); even so a key is captured the second time
-            # it shows up, so a buffer used once costs nothing extra
-            if key not in self._seen:
-                if len(self._seen) >= 64:
-                    self._seen.clear()
-                self._seen.add(key)
-                return self._step_eager(batch, True)
-            dev = batch.states.x.device
-            if len(self._graphs) >= 16:
-                self._graphs.pop(next(iter(self._graphs)))
-            # eager warm-up on a side stream (allocations, attribute set-up), on copies of nothing: one real step
-            loss = self._step_eager(batch, True, device_step=True, defer_bookkeeping=False)
-            if self._graph_key(batch) != key:     # that step flipped the select branch / crossed an lr milestone:
-                return loss                       # the branch it leads into is captured when it is first needed
-            sel = 0 if self.select else 1
-            net, other = self.nets[sel], self.nets[1 - sel]
-            torch.cuda.current_stream(dev).synchronize()
-            # the captured region refreshes the selected net's derived weights first, whatever the host thinks of them
+    def _capture(self, batch, key, r):
+        """Capture the four segments on these minibatch buffers (the second time the buffers show up: minibatches that
+        are freshly allocated every step never get here).  Host-side state the kernels would bake into their arguments
+        stays out of the graphs: Adam's step count lives on the device, the learning rate and the select branch are part
+        of the key.  Capturing records work without running it; the caller replays the segments right away."""
+        sel, args, mode, index, other, o_args = r
+        dev = batch.states.x.device
+        net = self.nets[sel]
+        torch.cuda.synchronize(dev)
+        if len(self._graphs) >= 16:
+            self._graphs.pop(next(iter(self._graphs)))
+        other._staged_refresh()
+        net._staged_refresh()
+        scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        entry = {"batch": batch, "loss": loss, "scalar": scalar}
+        L = _lib.lib()
+        n0 = int(L.mdq_launch_count())
+        pool = torch.cuda.graph_pool_handle()
+        for name in ("H", "A", "T", "U"):
             g = torch.cuda.CUDAGraph()
-            n0 = int(_lib.lib().mdq_launch_count())
-            state = (self.select, self.num_grads, self._state[sel]["step"])
-            other._staged_refresh()
-            net._stg_wver = None          # force the tile refresh of the selected net into the captured region
-            with torch.cuda.graph(g):
-                out = self._step_eager(batch, True, device_step=True, defer_bookkeeping=True, in_capture=True)
-            net._stg_wver = None          # ... which only recorded it: the tiles are still stale on the host's books
-            n_launch = int(_lib.lib().mdq_launch_count()) - n0
-            _lib.lib().mdq_launch_count_add(-n_launch)      # recorded, not run
-            entry = self._graphs[key] = [g, out, batch, n_launch]   # the batch is kept alive: the graph reads its buffers
-            # the capture pass only recorded work: nothing ran, host counters were not advanced (defer_bookkeeping)
-            assert state == (self.select, self.num_grads, self._state[sel]["step"])
-            return loss
-        other._staged_refresh()           # no-op unless the other net's weights changed since its tiles were built
-        entry[0].replay()
-        _lib.lib().mdq_launch_count_add(entry[3])
-        self._after_step(net, sel)
-        return entry[1]
-
-    def _after_step(self, net, sel):
-        net._bump_weights()               # raw-pointer write: derived weight copies (TF32 hi/lo tiles) are stale now
-        self._state[sel]["step"] += 1
-        self.num_grads += 1
-        if self.num_grads % self.target_update == 0:
-            self.select = not self.select
+            with torch.cuda.graph(g, pool=pool):
+                if name == "H":
+                    self._seg_H(batch, r, scalar, loss)
+                elif name == "A":
+                    entry["q_other"] = self._seg_A(r)
+                elif name == "T":
+                    self._seg_T(batch, r, entry["q_other"], scalar, loss, 2)
+                else:
+                    self._seg_U(sel)
+            entry[name] = g
+        entry["n"] = int(L.mdq_launch_count()) - n0
+        L.mdq_launch_count_add(-entry["n"])             # recorded, not run
+        net._staged_mark_fresh()                        # the forced refresh inside U was only recorded
+        self._graphs[key] = entry
+        return entry
 
     @torch.no_grad()
-    def _step_eager(self, batch: ReplayBatch, fused: bool = True, device_step: bool = False, defer_bookkeeping: bool = False,
-                    in_capture: bool = False):
-        """One step, launch by launch.
-
-        fused=True (default): forward of the NON-selected net only; the selected net's backward kernel
-        recomputes its own forward and evaluates the Huber term in place (mdq_qnet_replay_backward):
-        launches = forward + memset + backward + 2 weight-gradient + loss + Adam.
-        fused=False: the reference's literal sequence forward(Q1), forward(Q2), Huber, backward (used by tests).
-        """
+    def _step_serial(self, batch: ReplayBatch, fused: bool = True):
+        """One step, launch by launch on the current stream (timers, overlap off, the unfused reference sequence)."""
+        self.flush()
         net1, net2 = self.nets
         dev = batch.states.x.device
         L = _lib.lib()
         p = _lib.ptr
         B = int(batch.actions.shape[0])
-        s_args = net1._prep(batch.states)
-        n_args = net2._prep(batch.next_states) if batch.next_states is not None else None
+        sel, args, mode, index, other, o_args = self._roles(batch)
+        s_args = args if self.select else o_args
+        n_args = o_args if self.select else args
         n_next = int(n_args[4]) if n_args is not None else 0
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        sel = 0 if self.select else 1
         net = self.nets[sel]
         st = self._adam_state(sel)
         A = net._net.out_dim
-        if fused and (self.select or n_args is not None):
-            if self.select:
-                args, mode, index = s_args, 1, batch.next_slot
-                other, o_args = net2, n_args
-            else:
-                args, mode, index = n_args, 2, batch.owner
-                other, o_args = net1, s_args
+        if fused and args is not None:
             scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
-            # The selected net's stages 0 / 1 do not read Q_other: they go to a second stream and run beside the other
-            # net's forward, whose tail occupies few SMs (staged path only; the fused kernel does everything in phase 2).
-            overlap = self.overlap and o_args is not None and self.timers is None
-            if overlap:
-                main = torch.cuda.current_stream(dev)
-                if self._side is None:
-                    self._side = torch.cuda.Stream(dev)
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
-                    net._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, None, B,
-                                                self.gamma, scalar, loss, st["g"], phase=1)
             q_other = None
             if o_args is not None:
                 with self._timed("qnet_fwd"):
-                    q_other, _, _ = other._launch_forward(*o_args, False, False)
-            if overlap:
-                main.wait_stream(self._side)
+                    q_other = other._launch_forward(*o_args, False, False)[0]
             with self._timed("qnet_bwd+wgrad"):
                 net._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, q_other, B,
-                                            self.gamma, scalar, loss, st["g"], phase=2 if overlap else 0)
+                                            self.gamma, scalar, loss, st["g"])
         else:
             with self._timed("qnet_fwd"):
                 q1, _, _ = net1._launch_forward(*s_args, False, False)
@@ -436,25 +538,14 @@ class ReplayTrainer:
                                         None if self.select else p(gq), _lib.stream_ptr())
             _lib.check(rc, "mdq_huber_replay")
             if self.select or n_args is not None:
-                args = s_args if self.select else n_args
+                bargs = s_args if self.select else n_args
                 with self._timed("qnet_bwd+wgrad"):
-                    net._launch_backward(*args, gq, st["g"])
+                    net._launch_backward(*bargs, gq, st["g"])
             else:
                 st["g"].zero_()
-        n_used = net._n_used
-        if self.world > 1:
-            with self._timed("allreduce"):
-                torch.distributed.all_reduce(st["g"][:n_used], group=self.pg)
-        lr = multistep_lr(self.lr, self.num_grads)
-        # the step count lives on the device (st["step_dev"], advanced by the call) so that the same launch arguments
-        # serve every step -- eager and graph-replayed steps share one Adam kernel and one counter
-        with self._timed("adam"):
-            rc = L.mdq_adam_step_dev(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0],
-                                     self.betas[1], self.eps, self.wd, 1.0 / self.world, p(st["step_dev"]),
-                                     _lib.stream_ptr())
-        _lib.check(rc, "mdq_adam_step_dev")
-        if not defer_bookkeeping:
-            self._after_step(net, sel)
+        self._seg_U(sel, refresh=False)
+        net._pending = None
+        self._after_step(net, sel, fresh=False)
         return loss
 
 
