@@ -119,6 +119,7 @@ _SIGS = {
     "mdq_huber_replay": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P]),
     "mdq_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "mdq_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P, _P]),
+    "mdq_allreduce_adam": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, _P, c_int, c_int, _P, _P]),
     "mdq_scan_i32": (c_int, [_P, _P, c_int, _P]),
     "mdq_mesh_topology": (c_int, [_P, c_int, c_int] + [_P] * 14),
     "mdq_mesh_smooth": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),

@@ -1784,6 +1784,89 @@ __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__
 }
 __global__ void k_step_inc(int *step_dev) { step_dev[0] += 1; }
 
+// ------------------------------------------------------------------------------------------------
+// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel replay training).
+// Every rank owns a "stage" buffer that all peers have mapped (torch symmetric memory does the mapping; the
+// arithmetic and the synchronisation are here): [2][n] floats (two step parities) followed by `world` flag words.
+//   1. copy the local gradient into stage[parity] (own HBM), fence; the last block to finish raises this rank's flag
+//      (= step number, so flags never need resetting) in EVERY peer's flag row;
+//   2. every block waits until all `world` flags of its own row have reached this step;
+//   3. thread i sums the peers' stage[parity][i] over NVLink in rank order -- the same order on every rank, so all ranks
+//      hold bit-identical weights -- scales by 1/world and applies the Adam update in place.
+// One launch replaces ncclAllReduce (latency-bound at 0.5 MB: ~20-40 us at 2-8 ranks) + the Adam launch.  A stage
+// parity is rewritten two steps later, which a rank can only reach after every peer has finished reading it (it must
+// have seen their flags of the step in between).  All blocks are co-resident (grid <= 148 blocks of 256 threads).
+// ------------------------------------------------------------------------------------------------
+constexpr int AR_MAX_WORLD = 16;
+struct ArArgs {
+    float *stage[AR_MAX_WORLD];       // peer-mapped stage buffers, index = rank
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, float *__restrict__ p, const float *__restrict__ g,
+                                                           float *__restrict__ m, float *__restrict__ v, int64_t n, float lr,
+                                                           float b1, float b2, float eps, float wd,
+                                                           const int *__restrict__ step_dev, unsigned *block_counter)
+{
+    __shared__ float sh[2];
+    const int t = step_dev[0];
+    const unsigned seq = (unsigned)t + 1u;
+    const int64_t poff = (int64_t)(t & 1) * n;
+    float *mine = ar.stage[ar.rank];
+    if (threadIdx.x == 0) {
+        const double tt = (double)(t + 1);
+        const double bc1 = 1.0 - pow((double)b1, tt), bc2 = 1.0 - pow((double)b2, tt);
+        sh[0] = (float)((double)lr / bc1);
+        sh[1] = (float)sqrt(bc2);
+    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mine[poff + i] = g[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(block_counter, 1u) == gridDim.x - 1) {       // every block's share of the copy is visible
+            *block_counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < ar.world; ++r)
+                st_release_sys(reinterpret_cast<unsigned *>(ar.stage[r] + 2 * n) + ar.rank, seq);
+        }
+    }
+    if ((int)threadIdx.x < ar.world) {
+        const unsigned *flag = reinterpret_cast<const unsigned *>(mine + 2 * n) + threadIdx.x;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(flag) - seq) < 0)
+            if (++spins > (1u << 23)) __trap();     // (~10 s) a lost peer must fail loudly, never hang the device
+    }
+    __syncthreads();
+    const float step_size = sh[0], bc2_sqrt = sh[1];
+    const float gscale = 1.f / (float)ar.world;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gs = 0.f;
+        for (int r = 0; r < ar.world; ++r) gs += __ldcv(ar.stage[r] + poff + i);   // fixed rank order on every rank
+        float gi = gs * gscale;
+        const float pi = p[i];
+        gi = fmaf(wd, pi, gi);
+        const float m0 = m[i];
+        const float mi = fmaf(gi - m0, 1.f - b1, m0);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
 int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck, void (*kern)(const QArgs))
 {
     int rc = build_layout(*net, max_n, max_e, G, bwd, L, ck);
@@ -2010,6 +2093,29 @@ int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_a
     adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                               weight_decay, grad_scale, (float)((double)lr / bc1d), (float)sqrt(bc2d));
     return mdq::check_launch("adam_kernel");
+}
+
+int mdq_allreduce_adam(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int32_t *step_dev,
+                       const uint64_t *h_peer_stage, int rank, int world, uint32_t *block_counter, void *stream)
+{
+    if (!params || !grad || !exp_avg || !exp_avg_sq || !step_dev || !h_peer_stage || !block_counter || n < 1 || world < 1 ||
+        world > AR_MAX_WORLD || rank < 0 || rank >= world) {
+        mdq::set_error("mdq_allreduce_adam: bad argument");
+        return MDQ_EINVAL;
+    }
+    ArArgs ar;
+    memset(&ar, 0, sizeof(ar));
+    for (int r = 0; r < world; ++r) ar.stage[r] = reinterpret_cast<float *>(h_peer_stage[r]);
+    ar.rank = rank; ar.world = world;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 132) blocks = 132;          // every block must be resident while it waits for the peers' flags
+    allreduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ar, params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                    eps, weight_decay, step_dev, block_counter);
+    int rc = mdq::check_launch("allreduce_adam_kernel");
+    if (rc != MDQ_OK) return rc;
+    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    return mdq::check_launch("k_step_inc");
 }
 
 int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,

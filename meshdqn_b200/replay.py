@@ -265,7 +265,7 @@ class _Timed:
 
 class ReplayTrainer:
     def __init__(self, policy_net_1, policy_net_2, lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50,
-                 betas=(0.9, 0.999), eps=1e-8, process_group=None, graphs=False):
+                 betas=(0.9, 0.999), eps=1e-8, process_group=None, graphs=False, fused_allreduce=True):
         self.nets = (policy_net_1, policy_net_2)
         self.lr, self.wd, self.gamma = float(lr), float(weight_decay), float(gamma)
         self.betas, self.eps = betas, float(eps)
@@ -287,6 +287,11 @@ class ReplayTrainer:
         self.graphs = bool(graphs)
         self._graphs = {}
         self._seen = set()
+        # world > 1: gradient all-reduce + Adam as ONE kernel over NVLink peer memory (mdq_allreduce_adam) when torch's
+        # symmetric memory can map the stage buffers (NCCL all-reduce + Adam otherwise, or with fused_allreduce=False)
+        self.fused_allreduce = False
+        if self.world > 1 and fused_allreduce and next(policy_net_1.parameters()).is_cuda:
+            self._setup_symmetric()
 
     # -- helpers ----------------------------------------------------------------------------
     def _adam_state(self, i):
@@ -297,6 +302,31 @@ class ReplayTrainer:
             self._state[i] = dict(m=z, v=z.clone(), g=torch.zeros_like(net._flat), step=0,
                                   step_dev=torch.zeros(1, dtype=torch.int32, device=net._flat.device))
         return self._state[i]
+
+    def _setup_symmetric(self):
+        """Map one stage buffer per net on every peer (collective: the same order on every rank)."""
+        import ctypes
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            rank = dist.get_rank(group)
+            for i, net in enumerate(self.nets):
+                st = self._adam_state(i)
+                n = net._n_used
+                stage = symm.empty(2 * n + 64, dtype=torch.float32, device=net._flat.device)
+                stage.zero_()
+                hdl = symm.rendezvous(stage, group)
+                ptrs = (ctypes.c_uint64 * self.world)(*[int(x) for x in hdl.buffer_ptrs])
+                st.update(stage=stage, hdl=hdl, peer_ptrs=ptrs, rank=rank,
+                          counter=torch.zeros(1, dtype=torch.int32, device=net._flat.device))
+            torch.cuda.synchronize()
+            dist.barrier(group)                 # every rank's flags are zero before anyone raises one
+            self.fused_allreduce = True
+        except Exception as err:                # no peer mapping on this box: the NCCL path is the same arithmetic
+            import warnings
+            warnings.warn(f"fused all-reduce + Adam unavailable ({err}); using NCCL all_reduce + mdq_adam_step_dev")
+            self.fused_allreduce = False
 
     def _timed(self, name):
         return _Timed(self, name) if self.timers is not None else _NO_TIMER
@@ -358,10 +388,19 @@ class ReplayTrainer:
         net, st = self.nets[sel], self._adam_state(sel)
         n_used = net._n_used
         L, p = _lib.lib(), _lib.ptr
+        lr = multistep_lr(self.lr, self.num_grads)
+        if self.world > 1 and self.fused_allreduce:
+            with self._timed("allreduce+adam"):
+                rc = L.mdq_allreduce_adam(p(net._flat), p(st["g"]), p(st["m"]), p(st["v"]), n_used, lr, self.betas[0],
+                                          self.betas[1], self.eps, self.wd, p(st["step_dev"]), st["peer_ptrs"], st["rank"],
+                                          self.world, p(st["counter"]), _lib.stream_ptr())
+            _lib.check(rc, "mdq_allreduce_adam")
+            if refresh:
+                net._staged_refresh(force=True)
+            return
         if self.world > 1:
             with self._timed("allreduce"):
                 torch.distributed.all_reduce(st["g"][:n_used], group=self.pg)
-        lr = multistep_lr(self.lr, self.num_grads)
         # the step count lives on the device (st["step_dev"], advanced by the call) so that the same launch arguments
         # serve every step -- eager and graph-replayed steps share one Adam kernel and one counter
         with self._timed("adam"):
