@@ -234,6 +234,15 @@ class Env2DAirfoil:
             # (<plot_dir>/snapshots/save_velocities.npy [T, V0+E0, 2], save_pressures.npy [T, V0]; this package's P2
             # layout -- vertex dofs, then edge-midpoint dofs in lexicographic edge order -- not DOLFIN's dof numbering)
             u, p = np.load(u), np.load(p)
+            self.dof_map = None
+            if ap.get("dof_map"):
+                # files written by the REFERENCE (FEniCS): u.vector().get_local() rows in DOLFIN's dof order
+                # (Env2DAirfoil.py:139-150).  agent_params['dof_map'] = npz with DOLFIN's own dof coordinates (see
+                # meshdqn_b200/snapshots.py) turns them into this package's layout.  NOTE: those coordinates belong to
+                # the mesh the solve ran on, i.e. the smoothed M0 -- the same mesh fs.mesh holds here.
+                from .snapshots import DolfinDofMap
+                self.dof_map = DolfinDofMap.load(ap["dof_map"], fs.mesh.coordinates(), fs.mesh.edges.cpu().numpy())
+                u, p = self.dof_map.velocities(u), self.dof_map.pressures(p)
         if isinstance(u, int) and u == -1:
             if "synthetic_fields" in ap:
                 from .synthetic import synthetic_fields
@@ -287,13 +296,18 @@ class Env2DAirfoil:
         return self._pressures
 
     def set_plot_dir(self, plot_dir):
-        """Env2DAirfoil.py:432-449: snapshot .npy files (dof order is this package's P2 layout)."""
+        """Env2DAirfoil.py:432-449: snapshot .npy files -- this package's P2 layout, or DOLFIN's dof order when the
+        environment was built from DOLFIN-ordered files with a dof map."""
         self.plot_dir = plot_dir
         os.makedirs(plot_dir + "/snapshots", exist_ok=True)
         np.save(plot_dir + "/snapshots/velocities.npy", self.velocities)
         np.save(plot_dir + "/snapshots/pressures.npy", self.pressures)
-        np.save(plot_dir + "/snapshots/save_velocities.npy", self.original_u.cpu().numpy())
-        np.save(plot_dir + "/snapshots/save_pressures.npy", self.original_p.cpu().numpy())
+        U0, P0 = self.original_u.cpu().numpy(), self.original_p.cpu().numpy()
+        dm = getattr(self, "dof_map", None)
+        if dm is not None:      # the environment was fed DOLFIN-ordered files: write them back in the same order
+            U0, P0 = dm.dolfin_velocities(U0), dm.dolfin_pressures(P0)
+        np.save(plot_dir + "/snapshots/save_velocities.npy", U0)
+        np.save(plot_dir + "/snapshots/save_pressures.npy", P0)
 
     # ------------------------------------------------------------------ Env2DAirfoil.py:220-241
     def _get_distance_lookup(self):

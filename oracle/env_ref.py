@@ -208,7 +208,8 @@ class Env2DAirfoilRef:
         fs.remesh(coords, cells)
         pts = fs.topo.p2_points(fs.coords)
         cell_of, nmiss, d2 = geom.locate(pts, self.coords0, self.topo0.cells)
-        if self.interp_strict_tol is not None and nmiss and float(np.sqrt(d2.max())) > self.interp_strict_tol:
+        # farthest target dof point from the source mesh (0 when every point was located); a negative tolerance breaks always
+        if self.interp_strict_tol is not None and (float(np.sqrt(d2.max())) if nmiss else 0.0) > self.interp_strict_tol:
             fs.__dict__.update(old)                     # "INTERPOLATION BROKE": old mesh back, vertex back, code 2
             return 2
         u, p = geom.eval_fields(pts, fs.num_vertices, cell_of, self.coords0, self.topo0, self.U0, self.P0)

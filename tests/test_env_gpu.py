@@ -251,3 +251,58 @@ def test_snapshot_files_round_trip(cuda_device, tmp_path):
     assert torch.equal(env2.U, env.U) and torch.equal(env2.P, env.P) and np.array_equal(env2.gt_drag, env.gt_drag)
     s1, s2 = env.get_state(), env2.get_state()
     assert torch.equal(s1.x, s2.x) and torch.equal(s1.edge_index, s2.edge_index)
+
+
+def test_dolfin_ordered_snapshot_files(cuda_device, tmp_path):
+    """Snapshot files in DOLFIN's dof order (what the reference's FEniCS run writes, Env2DAirfoil.py:139-150) plus the
+    dof coordinates DOLFIN reports: the environment reproduces the one built from the package-layout arrays, and
+    set_plot_dir writes the files back in the order they came in."""
+    from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
+    from meshdqn_b200.snapshots import p2_points
+    coords, cells, U, P = oracle_fields("ah93w145")
+    cfg = make_config()
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    env = Env2DAirfoil(cfg, mesh=(coords, cells), device=cuda_device)
+    m = env.flow_solver.mesh
+    pts = p2_points(m.coordinates(), m.edges.cpu().numpy())         # dof points of the smoothed mesh the "solve" ran on
+    rng = np.random.RandomState(5)
+    order, p_order = rng.permutation(len(pts)), rng.permutation(m.nv)
+    np.savez(tmp_path / "dofmap.npz", xy_u=np.repeat(pts[order], 2, axis=0), comp_u=np.tile([0, 1], len(pts)),
+             xy_p=m.coordinates()[p_order])
+    np.save(tmp_path / "save_velocities.npy", U[:, order, :].reshape(U.shape[0], -1))
+    np.save(tmp_path / "save_pressures.npy", P[:, p_order])
+    cfg2 = make_config()
+    cfg2["agent_params"].update(u=str(tmp_path / "save_velocities.npy"), p=str(tmp_path / "save_pressures.npy"),
+                                dof_map=str(tmp_path / "dofmap.npz"))
+    env2 = Env2DAirfoil(cfg2, mesh=(coords, cells), device=cuda_device)
+    assert torch.equal(env2.U, env.U) and torch.equal(env2.P, env.P) and np.array_equal(env2.gt_drag, env.gt_drag)
+    s1, s2 = env.get_state(), env2.get_state()
+    assert torch.equal(s1.x, s2.x) and torch.equal(s1.edge_index, s2.edge_index)
+    env2.set_plot_dir(str(tmp_path / "plots"))
+    assert np.array_equal(np.load(tmp_path / "plots/snapshots/save_velocities.npy"), np.load(tmp_path / "save_velocities.npy"))
+    assert np.array_equal(np.load(tmp_path / "plots/snapshots/save_pressures.npy"), np.load(tmp_path / "save_pressures.npy"))
+
+
+@pytest.mark.parametrize("name", ["do_nothing", "strict_break", "out_of_vertices"])
+def test_special_paths_match_oracle_and_golden(cuda_device, name):
+    """Do-nothing steps (action 180: growing closest-window offset, reward recomputed on the unchanged mesh), a removal
+    that breaks (strict interpolation: code 2 -> reward -1, terminal, the old mesh restored) and running out of vertices
+    (Env2DAirfoil.py:330-364, 456-458, 569-573): the device environment against the oracle step by step and against the
+    committed golden file."""
+    z = np.load(os.path.join(GOLDEN, "special_ys930.npz"))
+    cfgs = {"do_nothing": {}, "strict_break": dict(interp_strict_tol=-1.0), "out_of_vertices": dict(N_closest=700)}
+    env, renv = make_envs("ys930", cuda_device, **cfgs[name])
+    s, rs = env.get_state(), renv.get_state()
+    assert torch.equal(s.x.cpu(), rs.x) and torch.equal(s.edge_index.cpu(), rs.edge_index)
+    for i, a in enumerate(z[f"{name}/actions"]):
+        s, r, done, _ = env.step(int(a))
+        rs, rr, rdone, _ = renv.step(int(a))
+        assert done == rdone == bool(z[f"{name}/dones"][i])
+        assert abs(r - rr) < 1e-9 and abs(r - z[f"{name}/rewards"][i]) < 1e-9
+        assert env.flow_solver.mesh.nv == renv.flow_solver.num_vertices == int(z[f"{name}/nvs"][i])
+        assert env.do_nothing_offset == renv.do_nothing_offset == int(z[f"{name}/offsets"][i])
+        assert torch.equal(s.x.cpu(), rs.x) and torch.equal(s.edge_index.cpu(), rs.edge_index)
+        assert checksum(s.x.cpu().numpy()) == z[f"{name}/x_checksums"][i]
+    if name == "strict_break":       # the broken removal left the environment on the old mesh
+        assert np.array_equal(env.flow_solver.mesh.coordinates(), renv.flow_solver.coords)
+        assert np.array_equal(env.flow_solver.removable, renv.flow_solver.removable)

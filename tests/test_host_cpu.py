@@ -245,3 +245,35 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_dolfin_dof_order_ingest_round_trip():
+    """Snapshot arrays in an arbitrary (DOLFIN-like) dof order come back in the package layout through the dof
+    coordinates DOLFIN reports (meshdqn_b200/snapshots.py); wrong meshes and non-permutations are refused."""
+    from conftest import load_mesh
+    from meshdqn_b200.snapshots import DolfinDofMap, p2_points
+    from meshdqn_b200.synthetic import synthetic_fields
+    from oracle import geom
+    coords, cells = load_mesh("ah93w145")
+    topo = geom.Topology(cells, len(coords))
+    U, P = synthetic_fields(coords, topo.edges, 3, 1)
+    pts = p2_points(coords, topo.edges)
+    rng = np.random.RandomState(0)
+    # a DOLFIN-like numbering: nodes in a random order, the two components of a node adjacent (x then y), plus an
+    # independent random order for the pressure space
+    node_order = rng.permutation(len(pts))
+    xy_u = np.repeat(pts[node_order], 2, axis=0)
+    comp_u = np.tile([0, 1], len(pts))
+    p_order = rng.permutation(len(coords))
+    xy_p = coords[p_order]
+    u_dolfin = U[:, node_order, :].reshape(3, -1)
+    p_dolfin = P[:, p_order]
+    dm = DolfinDofMap(coords, topo.edges, xy_u, comp_u, xy_p)
+    assert np.array_equal(dm.velocities(u_dolfin), U) and np.array_equal(dm.pressures(p_dolfin), P)
+    assert np.array_equal(dm.dolfin_velocities(U), u_dolfin) and np.array_equal(dm.dolfin_pressures(P), p_dolfin)
+    with pytest.raises(ValueError):
+        DolfinDofMap(coords + 1e-3, topo.edges, xy_u, comp_u, xy_p)           # another (moved) mesh
+    bad = xy_u.copy()
+    bad[1] = bad[3]
+    with pytest.raises(ValueError):
+        DolfinDofMap(coords, topo.edges, bad, comp_u, xy_p)                   # two dofs on one (point, component)

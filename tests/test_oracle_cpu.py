@@ -131,3 +131,29 @@ def test_golden_episode_oracle():
                 break
         assert acts == z["actions"].tolist()
         assert done and bool(z["dones"][-1])
+
+
+def test_golden_special_paths_oracle():
+    """Scripted episodes through the branches the greedy policy never takes: do-nothing (action 180), a broken removal
+    (strict interpolation -> code 2) and running out of vertices (tools/make_golden.py: SPECIAL)."""
+    import hashlib
+    sys_path_tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(sys_path_tools, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(os.path.join(GOLDEN, "special_ys930.npz"))
+    for name, sp in mg.SPECIAL.items():
+        coords, cells, U, P = oracle_fields("ys930")
+        cfg = make_config(**sp["cfg"])
+        cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+        env = Env2DAirfoilRef(cfg, mesh=(coords, cells))
+        env.get_state()
+        for i, a in enumerate(z[f"{name}/actions"]):
+            s, r, done, _ = env.step(int(a))
+            assert abs(r - z[f"{name}/rewards"][i]) < 1e-12 and done == bool(z[f"{name}/dones"][i])
+            assert env.flow_solver.num_vertices == int(z[f"{name}/nvs"][i])
+            assert mg.checksum(s.x.numpy()) == z[f"{name}/x_checksums"][i]
+    assert bool(z["strict_break/dones"][-1]) and z["strict_break/rewards"][-1] == -1.0 and z["strict_break/nvs"][-1] == 876
+    assert bool(z["out_of_vertices/dones"][-1]) and z["out_of_vertices/rewards"][-1] == -1.0
+    assert list(z["do_nothing/offsets"]) == [0, 1, 2, 2, 3, 3, 3, 4, 4]

@@ -87,7 +87,43 @@ def qnet_batch():
     print("qnet_batch", q.shape)
 
 
+SPECIAL = {
+    # scripted episodes for the branches a greedy policy does not visit:
+    #   do-nothing (action N_closest = 180, Env2DAirfoil.py:330-332: the closest-window offset grows, reward recomputed),
+    #   a broken removal (strict interpolation -> code 2, :569-573: old mesh back, reward -1, terminal),
+    #   running out of vertices (N_closest larger than the removable set, :355-357 / :456-458)
+    "do_nothing": dict(cfg={}, actions=[7, 180, 180, 23, 180, 0, 179, 180, 3]),
+    "strict_break": dict(cfg=dict(interp_strict_tol=-1.0), actions=[11]),
+    "out_of_vertices": dict(cfg=dict(N_closest=700), actions=[5]),
+}
+
+
+def special(short="ys930"):
+    out = {}
+    for name, spec in SPECIAL.items():
+        coords, cells, U, P = oracle_fields(short)
+        cfg = make_config(**spec["cfg"])
+        cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+        env = Env2DAirfoilRef(cfg, mesh=(coords, cells))
+        s = env.get_state()
+        rews, dones, nvs, xsum, esum, offs = [], [], [], [], [], []
+        for a in spec["actions"]:
+            s, r, done, _ = env.step(a)
+            rews.append(r); dones.append(done); nvs.append(env.flow_solver.num_vertices)
+            xsum.append(checksum(s.x.numpy())); esum.append(checksum(s.edge_index.numpy())); offs.append(env.do_nothing_offset)
+            if done:
+                break
+        out.update({f"{name}/actions": np.array(spec["actions"][:len(rews)]), f"{name}/rewards": np.array(rews),
+                    f"{name}/dones": np.array(dones), f"{name}/nvs": np.array(nvs), f"{name}/x_checksums": np.array(xsum),
+                    f"{name}/edge_checksums": np.array(esum), f"{name}/offsets": np.array(offs)})
+        print(short, name, "rewards", rews, "dones", dones, "nv", nvs)
+    np.savez_compressed(os.path.join(GOLDEN, f"special_{short}.npz"), **out)
+
+
 if __name__ == "__main__":
+    special("ys930")
+    if "--special-only" in sys.argv:
+        sys.exit(0)
     episode("ys930")
     episode("ah93w145")
     qnet_batch()
