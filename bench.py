@@ -336,7 +336,7 @@ def run_ours(args):
     # D2H + event) while step k+1 is already enqueued -- the public training-loop API a user would call ----
     from meshdqn_b200.replay import DevicePrefetcher
     pf = DevicePrefetcher(dev, static=True)   # two persistent device arenas: fixed addresses for the captured step
-    loss_host = torch.zeros(K + 4, dtype=torch.float32).pin_memory()
+    loss_host = torch.zeros(max(K, 8) + 4, dtype=torch.float32).pin_memory()
 
     def e2e_loop(n):
         pf.submit(rb_host)

@@ -253,6 +253,16 @@ int mdq_mesh_smooth(double *coords, int nv, int nc, const int32_t *nbr_ptr, cons
                     const int32_t *vc_ptr, const int32_t *vc_idx, const int32_t *cells, const uint8_t *on_boundary,
                     int iters, int32_t *status, void *stream);
 
+/* Diagnostics only (tools/smooth_bench.py): clock64 / %globaltimer stamps of the last mdq_mesh_smooth launch --
+ * [0] kernel start, [1] sweep start, [2] sweep end (cycles); [4], [5] sweep start / end (ns); [6] level count. */
+int mdq_debug_smooth_trace(long long *out8);
+
+/* Diagnostics only (tests/test_env_gpu.py): the branch-free division / square-root sequences of the smoothing sweep
+ * against the compiler's `/` and sqrt() on n pseudo-random operand pairs (mode 0: any finite bit pattern, mode 1:
+ * exponents within +-40 of 1.0).  counts4 (device): [0] accepted quotients that differ, [1] accepted roots that differ,
+ * [2], [3] operands the sequences declined (k_smooth redoes those with the ordinary operators). */
+int mdq_debug_fast_math_check(uint64_t seed, int64_t n, int mode, uint64_t *counts4, void *stream);
+
 /* FlowSolver.mark_boundaries (flow_solver.py:9-30,194-226): tags [ne] i32 (4 default, 0 walls, 1 airfoil,
  * 2 inflow, 3 outflow) and the removable mask (flow_solver.py:75-78,247-250; numpy `coord not in B`) [nv] u8. */
 int mdq_mesh_tags_removable(const double *coords, int nv, const int32_t *edges, const int32_t *edge_ncells, int ne,

@@ -376,6 +376,9 @@ class Env2DAirfoil:
         if not valid.all():
             print("OUT OF VERTICES")
             self.out_of_vertices = True
+            # the reference's feature assignment raises on a short window (Env2DAirfoil.py:284-286 assigns [k, .] into
+            # [N, .]); the oracle defines the state as all-zero features there and so does the device path
+            x.zero_()
         self.removable = np.argwhere(fs.removable)[:, 0]
         self.coord_map = {int(k): int(v) for k, v in enumerate(cm) if v >= 0}
         self.inv_coord_map = {v: k for k, v in self.coord_map.items()}

@@ -371,7 +371,10 @@ class _FusedQNet(nn.Module):
         """A trainer may still have this net's update in flight on its update stream (ReplayTrainer, segment U)."""
         ev = self.__dict__.get("_pending")
         if ev is not None:
-            torch.cuda.current_stream(dev).wait_event(ev)
+            if ev.query():                       # already finished: nothing to order against (and a capture in
+                self.__dict__["_pending"] = None  # progress could not wait on uncaptured work anyway)
+            else:
+                torch.cuda.current_stream(dev).wait_event(ev)
 
     def _staged_ws(self, B, max_n, max_e, backward, dev, shared=False):
         """Workspace of the staged launches, one per (stream, direction): replicas share a net across streams.

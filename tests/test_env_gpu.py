@@ -306,3 +306,25 @@ def test_special_paths_match_oracle_and_golden(cuda_device, name):
     if name == "strict_break":       # the broken removal left the environment on the old mesh
         assert np.array_equal(env.flow_solver.mesh.coordinates(), renv.flow_solver.coords)
         assert np.array_equal(env.flow_solver.removable, renv.flow_solver.removable)
+
+
+def test_fast_div_sqrt_match_operators(cuda_device):
+    """The smoothing sweep's branch-free division / square root (geom.cu: fast_div, fast_sqrt) are bit-identical to the
+    compiler's ``/`` and ``sqrt()`` wherever they accept their operands -- 2^28 pairs of arbitrary finite bit patterns and
+    2^28 pairs in the magnitude range of mesh coordinates -- and they accept essentially all of the latter."""
+    import ctypes
+    from meshdqn_b200 import _lib
+    L = _lib.lib()
+    L.mdq_debug_fast_math_check.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L.mdq_debug_fast_math_check.restype = ctypes.c_int
+    n = 1 << 28
+    for mode in (0, 1):
+        counts = torch.zeros(4, dtype=torch.int64, device=cuda_device)
+        with torch.cuda.device(cuda_device):
+            _lib.check(L.mdq_debug_fast_math_check(12345 + mode, n, mode, _lib.ptr(counts), _lib.stream_ptr()))
+        bad_div, bad_sqrt, decl_div, decl_sqrt = counts.cpu().tolist()
+        assert bad_div == 0 and bad_sqrt == 0, (mode, bad_div, bad_sqrt)
+        if mode == 1:
+            assert decl_div == 0 and decl_sqrt == 0, (decl_div, decl_sqrt)
+        else:
+            assert decl_div < n and decl_sqrt < n

@@ -10,6 +10,17 @@ for name in ("ys930", "ah93w145"):
     coords, cells = load_mesh(name)
     m = DeviceMesh(coords, cells, dev)
     c0 = m.coords.clone()
+    val = (m.nbr_ptr[1:] - m.nbr_ptr[:-1]).cpu().numpy()
+    ob = m.on_boundary.cpu().numpy().astype(bool)
+    print(f"{name}: valence histogram of interior vertices {np.bincount(val[~ob]).tolist()}", flush=True)
+    for it in (0, 10):
+        ts = []
+        for _ in range(5):
+            m.coords.copy_(c0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); m.smooth(it); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        print(f"{name}: smooth({it}) median {np.median(ts):.3f} ms", flush=True)
     ts = []
     for _ in range(12):
         m.coords.copy_(c0)
@@ -17,3 +28,9 @@ for name in ("ys930", "ah93w145"):
         e0.record(); m.smooth(50); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print(f"{name}: smooth(50) median {np.median(ts):.3f} ms  min {np.min(ts):.3f} ms  (nv {m.nv})", flush=True)
+    import ctypes
+    from meshdqn_b200 import _lib
+    buf = (ctypes.c_longlong * 8)()
+    L = _lib.lib(); L.mdq_debug_smooth_trace.argtypes = [ctypes.c_void_p]; L.mdq_debug_smooth_trace(buf)
+    t = list(buf)
+    print(f"  trace: setup {t[1]-t[0]} cyc, sweep {t[2]-t[1]} cyc = {t[5]-t[4]} ns -> {(t[2]-t[1])/max(1,(t[5]-t[4])):.3f} GHz, D {t[6]}, cyc/round {(t[2]-t[1])/(50*max(1,t[6])):.0f}", flush=True)
