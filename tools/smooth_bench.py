@@ -6,7 +6,10 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_mesh
 from meshdqn_b200.flow_solver import DeviceMesh
 dev = torch.device("cuda:0")
-for name in ("ys930", "ah93w145"):
+VARS = [int(v) for v in os.environ.get("SMOOTH_VARS", "0").split(",")]
+for name, var in [(n, v) for n in ("ys930", "ah93w145") for v in VARS]:
+    os.environ["MDQ_SMOOTH_VAR"] = str(var)
+    print(f"---- variant {var}", flush=True)
     coords, cells = load_mesh(name)
     m = DeviceMesh(coords, cells, dev)
     c0 = m.coords.clone()
@@ -27,6 +30,10 @@ for name in ("ys930", "ah93w145"):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); m.smooth(50); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
+    REF = globals().setdefault("REF", {})
+    if name not in REF:
+        REF[name] = m.coords.clone()
+    print(f"{name}: variant {var} result bit-identical to the first variant: {bool(torch.equal(REF[name], m.coords))}", flush=True)
     print(f"{name}: smooth(50) median {np.median(ts):.3f} ms  min {np.min(ts):.3f} ms  (nv {m.nv})", flush=True)
     import ctypes
     from meshdqn_b200 import _lib
