@@ -275,13 +275,14 @@ def run_reference(args):
 def run_ours(args):
     from meshdqn_b200 import _lib
     from meshdqn_b200.airfoilgcnn import NodeRemovalNet
-    from meshdqn_b200.parallel import init_from_env, max_over_ranks
+    from meshdqn_b200.parallel import bind_to_gpu_numa_node, init_from_env, max_over_ranks
     from meshdqn_b200.replay import ReplayBatch, ReplayTrainer
     import torch.distributed as dist
 
     rank, local, world = init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None    # pinned staging pages next to this rank's GPU
     L = _lib.lib()
     K, W = args.steps, max(args.warmup, 3)
 
@@ -466,7 +467,8 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(world), **({"setup": "fast-setup: random graphs (profiling run, not a bench value)"} if args.fast_setup else {})),
                 "clocks": clk.summary(),
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rb_host.h2d_bytes()), "d2h_bytes_per_step": 4},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rb_host.h2d_bytes()), "d2h_bytes_per_step": 4,
+                        "host_numa_node_rank0": numa},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm",
                              "kernel": "backward group of the selected net: k_stage0<save> + k_stage1<save> (tcgen05) + k_tail<bwd> + "

@@ -215,10 +215,13 @@ int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *e
 /* Fused gradient all-reduce + Adam over NVLink peer memory: ONE launch replaces the NCCL all-reduce of the flat
  * gradient (/root/reference/airfoil_dqn.py:326-336 ships it through the Ray object store) and the optimizer step.
  *   h_peer_stage (HOST array [world]): device addresses of every rank's stage buffer as mapped in THIS process
- *     (peer memory; 2 * n floats + `world` 32-bit flag words each, zero before the first call);
+ *     (peer memory, 16-byte aligned, mdq_allreduce_stage_floats(n, world) floats each, zero before the first call);
  *   grad: this rank's gradient (sum over its own transitions); the update uses mean over ranks = sum / world, summed in
  *     rank order on every rank (bit-identical weights everywhere);
- *   step_dev: as mdq_adam_step_dev; block_counter: device uint32, zero before the first call. */
+ *   step_dev: as mdq_adam_step_dev; block_counter: TWO device uint32, zero before the first call.
+ * Two-shot exchange of posted stores: gradient slices to their owners, reduced slices back to everyone (2 (world-1)/world
+ * x 4n bytes per rank over NVLink); every wait polls local memory. */
+int64_t mdq_allreduce_stage_floats(int64_t n, int world);
 int mdq_allreduce_adam(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int32_t *step_dev,
                        const uint64_t *h_peer_stage, int rank, int world, uint32_t *block_counter, void *stream);

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, Structure, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
@@ -119,6 +119,9 @@ _SIGS = {
     "mdq_huber_replay": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P]),
     "mdq_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "mdq_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P, _P]),
+    "mdq_allreduce_stage_floats": (c_int64, [c_int64, c_int]),
+    "mdq_debug_smooth_trace": (c_int, [_P]),
+    "mdq_debug_fast_math_check": (c_int, [c_uint64, c_int64, c_int, _P, _P]),
     "mdq_allreduce_adam": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, _P, c_int, c_int, _P, _P]),
     "mdq_scan_i32": (c_int, [_P, _P, c_int, _P]),
     "mdq_mesh_topology": (c_int, [_P, c_int, c_int] + [_P] * 14),

@@ -1814,6 +1814,40 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Two-shot, push-only exchange (all remote traffic is posted stores, every wait polls LOCAL memory):
+//   1. every rank writes slice j of its gradient into rank j's inbox [parity][sender][chunk], then raises flag1 on all ranks;
+//   2. rank j adds its inbox in RANK ORDER (the one summation order every element sees, on whichever rank it is reduced)
+//      and writes the reduced slice into every rank's result vector [parity][world * chunk], then raises flag2;
+//   3. every rank runs Adam over the whole vector from its local copy of the reduced gradient.
+// Per rank 2 * (world - 1) / world * 4n bytes cross NVLink (one-shot pulling: (world - 1) * 4n).  Stage layout in floats:
+// inbox at 0 (2 * npad), result at 2 * npad (2 * npad), flag words at 4 * npad (2 x AR_MAX_WORLD), npad = world * chunk.
+__device__ __forceinline__ float4 ld_cv4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ar_signal_and_wait(const ArArgs &ar, unsigned *counter, int which, int64_t npad, unsigned seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {       // every block's stores of this phase are visible
+            *counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < ar.world; ++r)
+                st_release_sys(reinterpret_cast<unsigned *>(ar.stage[r] + 4 * npad) + which * AR_MAX_WORLD + ar.rank, seq);
+        }
+    }
+    if ((int)threadIdx.x < ar.world) {
+        const unsigned *flag = reinterpret_cast<const unsigned *>(ar.stage[ar.rank] + 4 * npad) + which * AR_MAX_WORLD + threadIdx.x;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(flag) - seq) < 0)
+            if (++spins > (1u << 23)) __trap();     // (~10 s) a lost peer must fail loudly, never hang the device
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, float *__restrict__ p, const float *__restrict__ g,
                                                            float *__restrict__ m, float *__restrict__ v, int64_t n, float lr,
                                                            float b1, float b2, float eps, float wd,
@@ -1822,48 +1856,62 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, fl
     __shared__ float sh[2];
     const int t = step_dev[0];
     const unsigned seq = (unsigned)t + 1u;
-    const int64_t poff = (int64_t)(t & 1) * n;
-    float *mine = ar.stage[ar.rank];
+    const int world = ar.world, rank = ar.rank;
+    const int64_t chunk = ((n + 4 * world - 1) / (4 * world)) * 4, npad = chunk * world;
+    const int64_t par = (int64_t)(t & 1) * npad;
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
     if (threadIdx.x == 0) {
         const double tt = (double)(t + 1);
         const double bc1 = 1.0 - pow((double)b1, tt), bc2 = 1.0 - pow((double)b2, tt);
         sh[0] = (float)((double)lr / bc1);
         sh[1] = (float)sqrt(bc2);
     }
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        mine[poff + i] = g[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(block_counter, 1u) == gridDim.x - 1) {       // every block's share of the copy is visible
-            *block_counter = 0u;
-            __threadfence_system();
-            for (int r = 0; r < ar.world; ++r)
-                st_release_sys(reinterpret_cast<unsigned *>(ar.stage[r] + 2 * n) + ar.rank, seq);
+    // 1. scatter: float4 i of my gradient belongs to rank i / (chunk / 4)
+    const int64_t c4 = chunk / 4;
+    for (int64_t i = gtid; i < npad / 4; i += gsz) {
+        const int64_t e = 4 * i;
+        float4 val;
+        if (e + 3 < n) val = *reinterpret_cast<const float4 *>(g + e);     // g is 16-byte aligned (a whole torch tensor)
+        else { val.x = e < n ? g[e] : 0.f; val.y = e + 1 < n ? g[e + 1] : 0.f; val.z = e + 2 < n ? g[e + 2] : 0.f; val.w = 0.f; }
+        const int owner = (int)(i / c4);
+        const int64_t off = (i - owner * c4) * 4;
+        *reinterpret_cast<float4 *>(ar.stage[owner] + par + (int64_t)rank * chunk + off) = val;
+    }
+    ar_signal_and_wait(ar, block_counter, 0, npad, seq);
+    // 2. reduce my slice in rank order, publish it to everyone
+    const float *inbox = ar.stage[rank] + par;
+    for (int64_t i = gtid; i < c4; i += gsz) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {
+            const float4 a = ld_cv4(inbox + (int64_t)r * chunk + 4 * i);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
+        for (int r = 0; r < world; ++r)
+            *reinterpret_cast<float4 *>(ar.stage[r] + 2 * npad + par + (int64_t)rank * chunk + 4 * i) = s;
     }
-    if ((int)threadIdx.x < ar.world) {
-        const unsigned *flag = reinterpret_cast<const unsigned *>(mine + 2 * n) + threadIdx.x;
-        unsigned spins = 0;
-        while ((int)(ld_acquire_sys(flag) - seq) < 0)
-            if (++spins > (1u << 23)) __trap();     // (~10 s) a lost peer must fail loudly, never hang the device
-    }
-    __syncthreads();
+    ar_signal_and_wait(ar, block_counter + 1, 1, npad, seq);
+    // 3. Adam over the whole vector
     const float step_size = sh[0], bc2_sqrt = sh[1];
-    const float gscale = 1.f / (float)ar.world;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float gs = 0.f;
-        for (int r = 0; r < ar.world; ++r) gs += __ldcv(ar.stage[r] + poff + i);   // fixed rank order on every rank
-        float gi = gs * gscale;
-        const float pi = p[i];
-        gi = fmaf(wd, pi, gi);
-        const float m0 = m[i];
-        const float mi = fmaf(gi - m0, 1.f - b1, m0);
-        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = pi - step_size * (mi / denom);
+    const float gscale = 1.f / (float)world;
+    const float *red = ar.stage[rank] + 2 * npad + par;
+    for (int64_t i = gtid; i < npad / 4; i += gsz) {
+        const float4 gs4 = ld_cv4(red + 4 * i);
+        const float gsv[4] = {gs4.x, gs4.y, gs4.z, gs4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = 4 * i + u;
+            if (e >= n) break;
+            float gi = gsv[u] * gscale;
+            const float pi = p[e];
+            gi = fmaf(wd, pi, gi);
+            const float m0 = m[e];
+            const float mi = fmaf(gi - m0, 1.f - b1, m0);
+            const float vi = fmaf(b2, v[e], (1.f - b2) * gi * gi);
+            m[e] = mi;
+            v[e] = vi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            p[e] = pi - step_size * (mi / denom);
+        }
     }
 }
 
@@ -2095,6 +2143,13 @@ int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_a
     return mdq::check_launch("adam_kernel");
 }
 
+int64_t mdq_allreduce_stage_floats(int64_t n, int world)
+{
+    if (n < 1 || world < 1 || world > AR_MAX_WORLD) return -1;
+    const int64_t chunk = ((n + 4 * world - 1) / (4 * world)) * 4;
+    return 4 * chunk * world + 2 * AR_MAX_WORLD;
+}
+
 int mdq_allreduce_adam(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int32_t *step_dev,
                        const uint64_t *h_peer_stage, int rank, int world, uint32_t *block_counter, void *stream)
@@ -2108,7 +2163,7 @@ int mdq_allreduce_adam(float *params, const float *grad, float *exp_avg, float *
     memset(&ar, 0, sizeof(ar));
     for (int r = 0; r < world; ++r) ar.stage[r] = reinterpret_cast<float *>(h_peer_stage[r]);
     ar.rank = rank; ar.world = world;
-    int blocks = (int)((n + 255) / 256);
+    int blocks = (int)((n / 4 + 255) / 256);
     if (blocks > 132) blocks = 132;          // every block must be resident while it waits for the peers' flags
     allreduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ar, params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                     eps, weight_decay, step_dev, block_counter);

@@ -314,12 +314,13 @@ class ReplayTrainer:
             for i, net in enumerate(self.nets):
                 st = self._adam_state(i)
                 n = net._n_used
-                stage = symm.empty(2 * n + 64, dtype=torch.float32, device=net._flat.device)
+                stage = symm.empty(int(_lib.lib().mdq_allreduce_stage_floats(n, self.world)), dtype=torch.float32,
+                                   device=net._flat.device)
                 stage.zero_()
                 hdl = symm.rendezvous(stage, group)
                 ptrs = (ctypes.c_uint64 * self.world)(*[int(x) for x in hdl.buffer_ptrs])
                 st.update(stage=stage, hdl=hdl, peer_ptrs=ptrs, rank=rank,
-                          counter=torch.zeros(1, dtype=torch.int32, device=net._flat.device))
+                          counter=torch.zeros(2, dtype=torch.int32, device=net._flat.device))
             torch.cuda.synchronize()
             dist.barrier(group)                 # every rank's flags are zero before anyone raises one
             self.fused_allreduce = True

@@ -312,11 +312,8 @@ def test_fast_div_sqrt_match_operators(cuda_device):
     """The smoothing sweep's branch-free division / square root (geom.cu: fast_div, fast_sqrt) are bit-identical to the
     compiler's ``/`` and ``sqrt()`` wherever they accept their operands -- 2^28 pairs of arbitrary finite bit patterns and
     2^28 pairs in the magnitude range of mesh coordinates -- and they accept essentially all of the latter."""
-    import ctypes
     from meshdqn_b200 import _lib
     L = _lib.lib()
-    L.mdq_debug_fast_math_check.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-    L.mdq_debug_fast_math_check.restype = ctypes.c_int
     n = 1 << 28
     for mode in (0, 1):
         counts = torch.zeros(4, dtype=torch.int64, device=cuda_device)

@@ -277,3 +277,29 @@ def test_dolfin_dof_order_ingest_round_trip():
     bad[1] = bad[3]
     with pytest.raises(ValueError):
         DolfinDofMap(coords, topo.edges, bad, comp_u, xy_p)                   # two dofs on one (point, component)
+
+
+def test_bind_to_gpu_numa_node_reads_sysfs(tmp_path):
+    """parallel.bind_to_gpu_numa_node: PCI address -> NUMA node -> that node's CPUs (intersected with what the
+    container allows); anything missing leaves the affinity alone."""
+    import os
+    from meshdqn_b200 import parallel
+    before = os.sched_getaffinity(0)
+    try:
+        cpus = sorted(before)
+        root = tmp_path / "sys"
+        (root / "bus/pci/devices/0000:1b:00.0").mkdir(parents=True)
+        (root / "bus/pci/devices/0000:1b:00.0/numa_node").write_text("1\n")
+        (root / "devices/system/node/node1").mkdir(parents=True)
+        half = cpus[: max(1, len(cpus) // 2)]
+        (root / "devices/system/node/node1/cpulist").write_text(",".join(str(c) for c in half) + ",100000-100003\n")
+        assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+        assert parallel._bind_numa_of_pci("0000:1b:00.0", str(root)) == 1
+        assert os.sched_getaffinity(0) == set(half)
+        os.sched_setaffinity(0, before)
+        assert parallel._bind_numa_of_pci("0000:ff:00.0", str(root)) is None          # unknown device
+        (root / "bus/pci/devices/0000:1b:00.0/numa_node").write_text("-1\n")            # single-node machine
+        assert parallel._bind_numa_of_pci("0000:1b:00.0", str(root)) is None
+        assert os.sched_getaffinity(0) == before
+    finally:
+        os.sched_setaffinity(0, before)

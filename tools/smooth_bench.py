@@ -38,6 +38,6 @@ for name, var in [(n, v) for n in ("ys930", "ah93w145") for v in VARS]:
     import ctypes
     from meshdqn_b200 import _lib
     buf = (ctypes.c_longlong * 8)()
-    L = _lib.lib(); L.mdq_debug_smooth_trace.argtypes = [ctypes.c_void_p]; L.mdq_debug_smooth_trace(buf)
+    L = _lib.lib(); L.mdq_debug_smooth_trace(buf)
     t = list(buf)
     print(f"  trace: setup {t[1]-t[0]} cyc, sweep {t[2]-t[1]} cyc = {t[5]-t[4]} ns -> {(t[2]-t[1])/max(1,(t[5]-t[4])):.3f} GHz, D {t[6]}, cyc/round {(t[2]-t[1])/(50*max(1,t[6])):.0f}", flush=True)
