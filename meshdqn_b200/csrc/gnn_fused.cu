@@ -1827,18 +1827,27 @@ __device__ __forceinline__ float4 ld_cv4(const float *p)
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// End of a phase: the LAST block to get here (all of the grid's stores of the phase are then ordered before its fence)
+// raises this rank's flag on every peer -- one fence, then `world` independent relaxed stores from `world` threads -- and
+// every block waits until all ranks' flags for this step have arrived in local memory.
 __device__ __forceinline__ void ar_signal_and_wait(const ArArgs &ar, unsigned *counter, int which, int64_t npad, unsigned seq)
 {
-    __threadfence_system();
-    __syncthreads();
+    __shared__ unsigned last;
+    __syncthreads();                 // the block's stores happen-before thread 0's fence (cumulative), one fence per block
     if (threadIdx.x == 0) {
-        if (atomicAdd(counter, 1u) == gridDim.x - 1) {       // every block's stores of this phase are visible
-            *counter = 0u;
-            __threadfence_system();
-            for (int r = 0; r < ar.world; ++r)
-                st_release_sys(reinterpret_cast<unsigned *>(ar.stage[r] + 4 * npad) + which * AR_MAX_WORLD + ar.rank, seq);
-        }
+        __threadfence_system();
+        const unsigned done = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (done) *counter = 0u;
+        last = done;
+        __threadfence_system();
     }
+    __syncthreads();
+    if (last && (int)threadIdx.x < ar.world)
+        st_relaxed_sys(reinterpret_cast<unsigned *>(ar.stage[threadIdx.x] + 4 * npad) + which * AR_MAX_WORLD + ar.rank, seq);
     if ((int)threadIdx.x < ar.world) {
         const unsigned *flag = reinterpret_cast<const unsigned *>(ar.stage[ar.rank] + 4 * npad) + which * AR_MAX_WORLD + threadIdx.x;
         unsigned spins = 0;
@@ -1860,6 +1869,10 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, fl
     const int64_t chunk = ((n + 4 * world - 1) / (4 * world)) * 4, npad = chunk * world;
     const int64_t par = (int64_t)(t & 1) * npad;
     const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+    long long *stamp = reinterpret_cast<long long *>(ar.stage[rank] + 4 * npad + 2 * AR_MAX_WORLD);
+#define AR_STAMP(k)                                                                             \
+    if (gtid == 0) { long long tn; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn)); stamp[k] = tn; }
+    AR_STAMP(0)
     if (threadIdx.x == 0) {
         const double tt = (double)(t + 1);
         const double bc1 = 1.0 - pow((double)b1, tt), bc2 = 1.0 - pow((double)b2, tt);
@@ -1877,7 +1890,9 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, fl
         const int64_t off = (i - owner * c4) * 4;
         *reinterpret_cast<float4 *>(ar.stage[owner] + par + (int64_t)rank * chunk + off) = val;
     }
+    AR_STAMP(1)
     ar_signal_and_wait(ar, block_counter, 0, npad, seq);
+    AR_STAMP(2)
     // 2. reduce my slice in rank order, publish it to everyone
     const float *inbox = ar.stage[rank] + par;
     for (int64_t i = gtid; i < c4; i += gsz) {
@@ -1889,7 +1904,9 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, fl
         for (int r = 0; r < world; ++r)
             *reinterpret_cast<float4 *>(ar.stage[r] + 2 * npad + par + (int64_t)rank * chunk + 4 * i) = s;
     }
+    AR_STAMP(3)
     ar_signal_and_wait(ar, block_counter + 1, 1, npad, seq);
+    AR_STAMP(4)
     // 3. Adam over the whole vector
     const float step_size = sh[0], bc2_sqrt = sh[1];
     const float gscale = 1.f / (float)world;
@@ -1913,6 +1930,8 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, fl
             p[e] = pi - step_size * (mi / denom);
         }
     }
+    AR_STAMP(5)
+#undef AR_STAMP
 }
 
 int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck, void (*kern)(const QArgs))
@@ -2147,7 +2166,7 @@ int64_t mdq_allreduce_stage_floats(int64_t n, int world)
 {
     if (n < 1 || world < 1 || world > AR_MAX_WORLD) return -1;
     const int64_t chunk = ((n + 4 * world - 1) / (4 * world)) * 4;
-    return 4 * chunk * world + 2 * AR_MAX_WORLD;
+    return 4 * chunk * world + 2 * AR_MAX_WORLD + 16;      // + 8 x 64-bit phase stamps of the last call (diagnostics)
 }
 
 int mdq_allreduce_adam(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
