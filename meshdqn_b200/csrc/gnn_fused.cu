@@ -43,6 +43,9 @@ struct QLay {
     int o_w1, o_cat1, o_big, o_cat2, o_xbuf, o_hbuf, o_e1s, o_e1d, o_csr, o_e2s, o_e2d;
     int o_rowptr, o_cursor, o_score, o_z, o_newid, o_parent, o_dis, o_seg, o_ecnt, o_racc, o_y, o_part;
     int o_dx, o_dp, o_dcat, o_dr, o_amax, o_tds, o_h1k, o_c1k;
+    // backward of a graph whose saved activations overflow shared memory (AirfoilGCNN, TopK 0.5, 180 nodes): the hidden
+    // rows (hbuf, h1k) live in a per-CTA slice of the global workspace instead (sp_words floats, L2-resident)
+    int spill, sp_h1k, sp_hbuf, sp_words;
     // weight stream: blocks >= 1 and the MLP read their weights from 16 KB shared-memory stages that one
     // thread fills with cp.async.bulk (TMA) in layer order, several chunks ahead of the consumers
     int nstage, o_stage[MAX_STAGE], o_mbar, nchunks;  // nstage == 0: weights are read straight from global memory
@@ -80,6 +83,7 @@ struct QArgs {
     int *amax_out;
     const float *gout;
     float *ws;
+    float *spill;            // backward: [B][L.sp_words] hidden rows when L.spill
     WDesc wd;
     WChunks ck;
     // fused replay gradient (rp_mode 0: grad_out given; 1: Huber through this net's Q(s)[a]; 2: through max_a Q(s'))
@@ -98,9 +102,10 @@ struct QArgs {
 // ------------------------------------------------------------------------------------------------
 int topk_count(float ratio, int n) { return (int)ceilf(ratio * (float)n); }
 
-int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck = nullptr)
+int build_layout_impl(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck, int spill)
 {
     memset(&L, 0, sizeof(L));
+    L.spill = spill;
     if (net.n_blocks < 1 || net.n_blocks > MAXB) return MDQ_EINVAL;
     if (net.width < 4 || net.width > 256 || (net.width & 3)) return MDQ_EINVAL;
     if (net.blk[0].type != MDQ_BLOCK_SAGE || net.blk[0].kin != net.in_dim) return MDQ_EINVAL;
@@ -189,13 +194,16 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
         L.o_dx = L.o_cat2 + mdq::pad4(gcap1 * 2 * W);
         L.o_dp = L.o_dx + mdq::pad4(L.xrows * W);
         L.o_dcat = L.o_dp + mdq::pad4(gcap1 * W);
-        L.o_h1k = take(gcap1 * W);      // block 0's kept hidden rows
+        L.sp_h1k = 0;
+        L.sp_hbuf = mdq::pad4(gcap1 * W);
+        L.sp_words = L.sp_hbuf + mdq::pad4(L.xrows * W);
+        L.o_h1k = spill ? 0 : take(gcap1 * W);      // block 0's kept hidden rows
         L.o_c1k = take(gcap1 * L.KC1);  // ... and their input rows [agg | x]
     }
     for (int i = 0; i < n_dedicated && L.nstage < MAX_STAGE; ++i) L.o_stage[L.nstage++] = take(STAGE_WORDS);
     L.o_mbar = 0;
     L.o_xbuf = take(L.xrows * W);
-    L.o_hbuf = take((bwd ? L.xrows : gcap1) * W);
+    L.o_hbuf = (bwd && spill) ? 0 : take((bwd ? L.xrows : gcap1) * W);
     // edge endpoints / CSR columns are CTA-local row ids < 65536: stored as 16-bit, two per word
     if (max_n > 65535 || gcap1 > 65535) return MDQ_ESMEM;
     L.o_e1s = take((L.e_max + 1) / 2);
@@ -250,6 +258,14 @@ int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLa
     if (overflow) return MDQ_ESMEM;
     L.nchunks = nck;
     return MDQ_OK;
+}
+
+// Shared memory first; a backward layout that does not fit the 227 KB of one CTA moves its hidden rows to the workspace.
+int build_layout(const mdq_net_t &net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck = nullptr)
+{
+    int rc = build_layout_impl(net, max_n, max_e, G, bwd, L, ck, 0);
+    if (rc == MDQ_OK && bwd && (size_t)L.total * 4 > 227 * 1024) rc = build_layout_impl(net, max_n, max_e, G, bwd, L, ck, 1);
+    return rc;
 }
 
 int build_wdesc(const mdq_net_t &net, int B, int max_n, WDesc &wd)
@@ -904,7 +920,9 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
     float *big = smem + L.o_big;
     float *cat2 = smem + L.o_cat2;
     float *xbuf = smem + L.o_xbuf;
-    float *hbuf = smem + L.o_hbuf;
+    float *spill = (BWD && L.spill) ? a.spill + (size_t)blockIdx.x * L.sp_words : nullptr;
+    float *hbuf = spill ? spill + L.sp_hbuf : smem + L.o_hbuf;
+    float *h1k = spill ? spill + L.sp_h1k : smem + L.o_h1k;
     eid_t *e1s = reinterpret_cast<eid_t *>(smem + L.o_e1s);
     eid_t *e1d = reinterpret_cast<eid_t *>(smem + L.o_e1d);
     eid_t *csr = reinterpret_cast<eid_t *>(smem + L.o_csr);
@@ -1082,7 +1100,7 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
             const int *par = parent + L.n_max + L.rowoff[1] + obase;
             if (L.fused) {
                 // recompute the hidden rows of the k kept nodes only (same code path, bit-identical)
-                float *hk = (BWD ? smem + L.o_h1k : hbuf) + (size_t)obase * W;
+                float *hk = (BWD ? h1k : hbuf) + (size_t)obase * W;
                 dense_rows<true>(k, KC1, cat1, KC1, w1s, w1s + KC1 * W, hk, W, W, true, par);
                 __syncthreads();
                 for (int idx = tid; idx < k * W; idx += NT) xo[idx] = hk[idx] * score[par[idx / W]];
@@ -1092,7 +1110,7 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
                     const int i = par[r];
                     const float h = big[(size_t)i * W + c];
                     xo[idx] = h * score[i];
-                    if (BWD) (smem + L.o_h1k)[(size_t)(obase + r) * W + c] = h;
+                    if (BWD) h1k[(size_t)(obase + r) * W + c] = h;
                 }
             }
             if (BWD)
@@ -1396,7 +1414,7 @@ __global__ void __launch_bounds__(NT, 2) qnet_kernel(const __grid_constant__ QAr
         const int n_b = (b == 0) ? (a.nptr[g + 1] - a.nptr[g]) : seg[b * (G + 1) + 1];
         const int k = seg[(b + 1) * (G + 1) + 1];  // kept rows (G == 1)
         // hidden rows of block b: block 0 keeps only its kept rows (compact, row r); blocks >= 1 keep all rows
-        const float *H = (b == 0) ? smem + L.o_h1k : hbuf + (size_t)L.hoff[b] * W;
+        const float *H = (b == 0) ? h1k : hbuf + (size_t)L.hoff[b] * W;
         const bool compactH = (b == 0);
         const int rbase = (b == 0) ? 0 : L.n_max + L.rowoff[b];
         const int *par = parent + L.n_max + L.rowoff[b + 1];
@@ -2053,6 +2071,22 @@ int64_t mdq_qnet_bwd_workspace_floats(const mdq_net_t *net, int n_graphs, int ma
         tasks += (int64_t)S * nkg;
     }
     (void)tasks;
+    // + every graph's spill slice (hidden rows of a backward layout that overflows shared memory; max_e does not enter)
+    QLay L;
+    if (build_layout(*net, max_n, 1, 1, 1, L) != MDQ_OK) return -1;
+    return (int64_t)wd.total + partial + 64 + (int64_t)n_graphs * L.sp_words;
+}
+
+static int64_t bwd_spill_offset(const WDesc &wd, int n_graphs)
+{
+    int64_t partial = 0;
+    for (int i = 0; i < wd.nl; ++i) {
+        const WLayer &l = wd.l[i];
+        if (l.rpg == 0) continue;
+        const int S = (n_graphs * l.rpg + WG_TASK - 1) / WG_TASK;
+        const int nkg = (l.K + 1 + WG_KG - 1) / WG_KG;
+        partial += (int64_t)S * nkg * WG_KG * l.C;
+    }
     return (int64_t)wd.total + partial + 64;
 }
 
@@ -2067,6 +2101,7 @@ static int qnet_backward_launch(const mdq_net_t *net, const float *params, const
     a.net = *net;
     a.params = params; a.x = x; a.esrc = (const long long *)edge_src; a.edst = (const long long *)edge_dst; a.nptr = node_ptr; a.eptr = edge_ptr;
     a.B = n_graphs; a.ws = workspace; a.trace = g_trace;
+    a.spill = workspace + bwd_spill_offset(a.wd, n_graphs);
     const WDesc &wd = a.wd;
     int n_tasks = 0;
     for (int i = 0; i < wd.nl; ++i) {

@@ -141,3 +141,160 @@ def train(make_env, net1, net2, *, episodes, batch_size=32, lr=1e-5, weight_deca
             handler.write()                                 # :490-491
             save_policy_nets(save_prefix, net1, net2)
     return handler
+
+
+class _EnvWorkers:
+    """R environments stepped concurrently: one host thread and one CUDA stream each (the device work of a step --
+    topology, the single-CTA smoothing sweep, re-interpolation, drag / lift, state build -- overlaps the other
+    replicas' kernels and their host-side Qhull calls, as in ``parallel.run_env_replicas``).  ``step_all(actions)``
+    returns when every environment has taken its step; results come back in replica order, so a run is reproducible
+    whatever the thread timing."""
+
+    def __init__(self, make_env, n_envs, device):
+        import threading
+        self.dev = torch.device(device)
+        self.on_gpu = self.dev.type == "cuda"
+        self.make_env = make_env
+        self.envs = [make_env() for _ in range(n_envs)]
+        self.states = [e.get_state() for e in self.envs]
+        if self.on_gpu:
+            torch.cuda.synchronize(self.dev)
+        self._go = threading.Barrier(n_envs + 1)
+        self._done = threading.Barrier(n_envs + 1)
+        self._actions = [0] * n_envs
+        self._results = [None] * n_envs
+        self._errors = []
+        self._stop = False
+        self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True) for i in range(n_envs)]
+        for t in self._threads:
+            t.start()
+
+    def _run(self, i):
+        import contextlib
+        stream = torch.cuda.Stream(self.dev) if self.on_gpu else None
+        ctx = (lambda: torch.cuda.stream(stream)) if self.on_gpu else contextlib.nullcontext
+        if self.on_gpu:
+            torch.cuda.set_device(self.dev)
+        while True:
+            try:
+                self._go.wait()
+            except Exception:
+                return
+            if self._stop:
+                return
+            try:
+                with ctx():
+                    self._results[i] = self.envs[i].step(self._actions[i])
+                    if stream is not None:
+                        stream.synchronize()
+            except Exception as exc:              # surfaced by step_all
+                self._errors.append(exc)
+            try:
+                self._done.wait()
+            except Exception:
+                return
+
+    def step_all(self, actions):
+        self._actions[:] = [int(a) for a in actions]
+        self._go.wait()
+        self._done.wait()
+        if self._errors:
+            raise self._errors[0]
+        return list(self._results)
+
+    def reset(self, i):
+        self.envs[i] = self.make_env()
+        self.states[i] = self.envs[i].get_state()
+
+    def close(self):
+        self._stop = True
+        try:
+            self._go.wait(timeout=5)
+        except Exception:
+            pass
+        for t in self._threads:
+            t.join(timeout=5)
+
+
+def train_replicas(make_env, net1, net2, *, n_envs, rounds, batch_size=32, lr=1e-5, weight_decay=1e-6, gamma=1.0,
+                   target_update=50, eps_start=1.0, eps_end=0.01, eps_decay=10000.0, memory_capacity=10000, device=None,
+                   save_prefix=None, seed=137, pg=None, handler=None, graphs=False, verbose=False):
+    """The reference's multi-worker actor loop (airfoil_dqn.py:428-503 run by ``NUM_WORKERS`` Ray actors, :508-520)
+    without Ray: ``n_envs`` environment replicas per process and -- under ``torchrun`` -- one process per GPU.
+
+    Every round (a) ONE batched Q-evaluation of ``net1`` scores all replicas' states (the reference's workers each
+    call ``select_action`` on the shared parameter server, :458-461), (b) the replicas take their epsilon-greedy
+    step concurrently (``_EnvWorkers``), (c) the transitions go to this process's device replay memory in replica
+    order, and (d) one optimisation step runs per environment step taken (:483, each worker's ``optimize_model``).
+    ``steps_done`` advances once per environment step of this process, as the reference's per-worker counter does.
+
+    Multi-GPU: with an initialised process group (``pg`` or the default group) ``ReplayTrainer`` averages the
+    gradients of all ranks every optimisation step, so every rank keeps bit-identical nets; ranks seed their
+    exploration and replay sampling with ``seed + rank``.  All ranks run the same number of rounds and start
+    optimising in the same round (same ``n_envs`` and ``batch_size``), so the collectives line up.
+
+    Returns this process's ``DataHandler`` (rank 0 writes the policy nets; every rank writes its own curves under
+    ``{save_prefix}rank{r}_`` when there is more than one).
+    """
+    import torch.distributed as dist
+    from .data import Batch
+    from .replay import DeviceReplayMemory, ReplayTrainer
+    dev = torch.device(device) if device is not None else next(net1.parameters()).device
+    world = dist.get_world_size(pg) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(pg) if world > 1 else 0
+    rng = np.random.RandomState(seed + rank)
+    pyrng = random.Random(seed + rank)
+    prefix = save_prefix
+    if prefix is not None and world > 1:
+        prefix = f"{save_prefix}rank{rank}_"
+    handler = handler or DataHandler(prefix or "./")
+    trainer = ReplayTrainer(net1, net2, lr=lr, weight_decay=weight_decay, gamma=gamma, target_update=target_update,
+                            process_group=pg, graphs=graphs)       # world > 1: gradients averaged over the ranks
+    workers = _EnvWorkers(make_env, n_envs, dev)
+    try:
+        n_actions = int(workers.envs[0].N_CLOSEST)
+        s0 = workers.states[0]
+        e_max = max(6 * int(s0.x.shape[0]), 2 * int(s0.edge_index.shape[1]))
+        memory = DeviceReplayMemory(memory_capacity, int(s0.x.shape[0]), e_max, int(s0.x.shape[1]), dev)
+        ep_actions = [[] for _ in range(n_envs)]
+        ep_rewards = [[] for _ in range(n_envs)]
+        steps_done = 0
+        for rnd in range(rounds):
+            with torch.no_grad():
+                greedy, _ = net1.select_action(Batch.from_data_list(workers.states).to(dev))
+            greedy = greedy.cpu().tolist()
+            actions, epss = [], []
+            for i in range(n_envs):
+                sample = rng.random_sample()
+                eps = epsilon_threshold(steps_done, eps_start, eps_end, eps_decay)
+                steps_done += 1
+                epss.append(eps)
+                actions.append(int(greedy[i]) if sample > eps else pyrng.sample(range(n_actions + 1), 1)[0])
+            results = workers.step_all(actions)
+            for i, (next_state, reward, done, _) in enumerate(results):
+                ep_actions[i].append(actions[i])
+                ep_rewards[i].append(reward)
+                memory.push(workers.states[i], actions[i], None if done else next_state, reward)
+                workers.states[i] = next_state
+                if done:
+                    handler.add_episode(ep_rewards[i], ep_actions[i])
+                    ep_actions[i], ep_rewards[i] = [], []
+                    workers.reset(i)
+            for i in range(n_envs):
+                if len(memory) >= batch_size:
+                    loss = float(trainer.step(memory.sample(batch_size, rng=rng)))
+                    handler.add_loss(loss)
+                handler.add_eps(epss[i])
+            if verbose and rank == 0:
+                print(f"round {rnd}: actions {actions} eps {epss[-1]:.3f} memory {len(memory)}")
+        trainer.flush()
+        for i in range(n_envs):                             # unfinished episodes are recorded as they stand
+            if ep_actions[i]:
+                handler.add_episode(ep_rewards[i], ep_actions[i])
+        if save_prefix is not None:
+            handler.write()
+            if rank == 0:
+                save_policy_nets(save_prefix, net1, net2)
+    finally:
+        workers.close()
+    return handler

@@ -303,3 +303,43 @@ def test_bind_to_gpu_numa_node_reads_sysfs(tmp_path):
         assert os.sched_getaffinity(0) == before
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_env_workers_step_in_replica_order():
+    """dqn._EnvWorkers: R environments stepped on R threads, results in replica order whatever the thread timing; errors
+    in a worker surface in the caller."""
+    import time
+    import pytest
+    from meshdqn_b200 import dqn
+
+    class FakeEnv:
+        made = 0
+
+        def __init__(self):
+            self.k = FakeEnv.made
+            FakeEnv.made += 1
+            self.t = 0
+
+        def get_state(self):
+            return (self.k, self.t)
+
+        def step(self, action):
+            if action < 0:
+                raise ValueError("bad action")
+            time.sleep(0.002 * ((7 * self.k) % 3))      # finish out of order
+            self.t += 1
+            return (self.k, self.t), float(action), self.t >= 2, {}
+
+    w = dqn._EnvWorkers(FakeEnv, 4, "cpu")
+    try:
+        assert w.states == [(0, 0), (1, 0), (2, 0), (3, 0)]
+        r = w.step_all([5, 6, 7, 8])
+        assert [x[0] for x in r] == [(0, 1), (1, 1), (2, 1), (3, 1)] and [x[1] for x in r] == [5.0, 6.0, 7.0, 8.0]
+        r = w.step_all([1, 1, 1, 1])
+        assert all(x[2] for x in r)
+        w.reset(2)
+        assert w.states[2] == (4, 0) and w.envs[2].k == 4
+        with pytest.raises(ValueError):
+            w.step_all([0, -1, 0, 0])
+    finally:
+        w.close()

@@ -112,3 +112,62 @@ def test_two_ranks_equal_one_rank(tmp_path):
     assert z["fused"][0] == z["nccl"][0] == z["fused_graph"][0]
     for i in range(2):
         assert torch.equal(z["fused"][1][i], z["nccl"][1][i]) and torch.equal(z["fused"][1][i], z["fused_graph"][1][i])
+
+
+def _actor_worker(rank, world, port, out_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import contextlib
+    import io
+    import torch.distributed as dist
+    from conftest import make_config, oracle_fields
+    from meshdqn_b200 import dqn
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    from meshdqn_b200.Env2DAirfoil import Env2DAirfoil
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    coords, cells, U, P = oracle_fields("ah93w145")
+    cfg = make_config()
+    cfg["agent_params"]["u"], cfg["agent_params"]["p"] = U, P
+    mk = lambda: Env2DAirfoil(cfg, mesh=(coords, cells), device=dev)
+    torch.manual_seed(1370)
+    nets = []
+    for _ in range(2):
+        n = NodeRemovalNet(181, conv_width=128, topk=0.1)
+        n.set_num_nodes(17)
+        nets.append(n.to(dev))
+    w0 = nets[0]._flat.clone() if getattr(nets[0], "_flat", None) is not None else None
+    with contextlib.redirect_stdout(io.StringIO()):
+        h = dqn.train_replicas(mk, nets[0], nets[1], n_envs=2, rounds=5, batch_size=4, eps_decay=8.0, target_update=3,
+                               memory_capacity=64, device=dev, save_prefix=out_path + "_", lr=1e-3)
+    torch.cuda.synchronize()
+    sd = {k: v.cpu() for k, v in nets[0].state_dict().items()}
+    torch.save({"sd": sd, "actions": h.actions, "losses": h.losses, "epss": h.epss}, out_path + f".rank{rank}.pt")
+    dist.barrier()
+    os._exit(0)
+
+
+def test_actor_loop_two_ranks_keep_identical_nets(tmp_path):
+    """dqn.train_replicas under a 2-rank NCCL group: each rank explores with its own replicas and replay memory, the
+    gradients are averaged every optimisation step, so both ranks end with bit-identical policy nets."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "actor")
+    port = 29800 + os.getpid() % 200
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_actor_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=150)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("actor-loop rank did not finish")
+        assert p.exitcode == 0
+    a, b = torch.load(out + ".rank0.pt"), torch.load(out + ".rank1.pt")
+    assert all(torch.equal(a["sd"][k], b["sd"][k]) for k in a["sd"])
+    assert len(a["losses"]) == len(b["losses"]) == 10 - 2 and a["actions"] != b["actions"]   # different exploration per rank
+    assert os.path.exists(out + "_policy_net_1.pt") and os.path.exists(out + "_rank1_eps.npy")

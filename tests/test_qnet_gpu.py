@@ -129,6 +129,32 @@ def test_airfoilgcnn_forward(cuda_device):
     assert (y - y_ref).abs().max() < 1e-5 * max(1.0, y_ref.abs().max().item())
 
 
+def test_airfoilgcnn_backward_matches_autograd_oracle(cuda_device):
+    """AirfoilGCNN (six blocks, TopK 0.5, scalar head; /root/reference/airfoilgcnn.py:148-209) trained through autograd:
+    parameter gradients of a weighted sum of the predictions against the oracle's autograd."""
+    from meshdqn_b200.airfoilgcnn import AirfoilGCNN
+    torch.manual_seed(5)
+    ref = gnn_ref.AirfoilGCNN(64)
+    net = AirfoilGCNN(64)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(cuda_device)
+    g = torch.Generator().manual_seed(19)
+    b = Batch.from_data_list([rand_graph(g, n=int(torch.randint(40, 181, (1,), generator=g))) for _ in range(12)])
+    w = torch.randn(12, 1, generator=g)
+    (ref(b) * w).sum().backward()
+    (net(b.to(cuda_device)) * w.to(cuda_device)).sum().backward()
+    rp = dict(ref.named_parameters())
+    checked = 0
+    for k, p in net.named_parameters():
+        gr = rp[k].grad
+        if gr is None:
+            continue
+        assert p.grad is not None, k
+        assert (p.grad.cpu() - gr).abs().max() <= 1e-4 * max(gr.abs().max().item(), 1e-6), k
+        checked += 1
+    assert checked >= 20
+
+
 def test_backward_matches_autograd_oracle(cuda_device):
     net, ref = make_nets(cuda_device, lively=True)
     g = torch.Generator().manual_seed(11)
