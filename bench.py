@@ -34,7 +34,11 @@ sys.path.insert(0, ROOT)
 # fixture mesh files; only the `cpu_baseline` legs and `--impl reference` (below) execute the oracle.
 
 BATCH = 256
-STAGED_GROUP_TRAFFIC = None      # filled from profiles/r02_ncu_staged_replay.md once captured
+# dram__bytes_read.sum + dram__bytes_write.sum per launch summed over the six kernels of the backward group, from the
+# `ncu --set full` capture summarised in profiles/r02_ncu_staged.txt: k_stage0<save> 5.44 + k_stage1<save> 2.73 + k_tail<bwd>
+# 1.77 + k_bwd1 3.49 + wgrad_partial 6.21 + wgrad_reduce 1.01 MB.  ncu invalidates the caches before every kernel, so each
+# one re-reads from DRAM the intermediates its predecessor left in L2 -- an upper bound on the step's real DRAM traffic.
+STAGED_GROUP_TRAFFIC = 20_645_000
 METRIC = "replay_train_graphs_per_s"
 UNIT = "graphs/s"
 
@@ -475,7 +479,7 @@ def run_ours(args):
                                        "k_bwd1 + wgrad_partial + wgrad_reduce",
                              "achieved": achieved, "peak": hbm, "peak_source": how, "unit": "GB/s", "frac": achieved / hbm,
                              # dram__bytes_read+write per launch, summed over the group, from one `ncu --set full` capture
-                             # (cold caches; profiles/r02_ncu_staged_replay.md)
+                             # (cold caches; profiles/r02_ncu_staged.txt)
                              "traffic": STAGED_GROUP_TRAFFIC,
                              "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": dom_us,
                              "note": "latency-bound by construction at 256 x 180-node graphs (15 KB per graph, 0.5 MB of weights): "
