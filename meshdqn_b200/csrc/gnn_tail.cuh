@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
             }
         }
         cta_sync();
+        STG_TRACE(a.trace, 96, 8);    // d2
         {
             float acc[1][4];
             dense_fwd<128, 1>(rg, 64, 128, y2, LDY2, 1, acc);
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
             }
         }
         cta_sync();
+        STG_TRACE(a.trace, 96, 9);    // d1
         {
             float acc[1][8];
             dense_fwd<256, 1>(rg, 128, 256, y1, LDW, 1, acc);
@@ -535,6 +537,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
                 }
         }
         cta_sync();
+        STG_TRACE(a.trace, 96, 10);   // dR
         // ---- block 3 backward: one row per graph, warp per graph ----
         {
             const float4 w = __ldg(reinterpret_cast<const float4 *>(P + a.p5_off) + lane);
@@ -553,6 +556,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
             }
         }
         cta_sync();
+        STG_TRACE(a.trace, 96, 11);   // pool5 backward
         {
             float acc[1][4];
             dense_fwd<128, 1>(rg, 128, 128, H4, LDW, 1, acc);
@@ -563,6 +567,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
             }
         }
         cta_sync();
+        STG_TRACE(a.trace, 96, 12);   // conv5^T
         // ---- block 2 backward: pooling through the one kept row, then A_hat^T ----
         {
             const float4 w = __ldg(reinterpret_cast<const float4 *>(P + a.p4_off) + lane);
@@ -602,6 +607,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
             }
         }
         cta_sync();
+        STG_TRACE(a.trace, 96, 13);   // pool4 backward + A_hat^T
         {
             float acc[4][4];
             dense_fwd<128, 4>(rg, 128, 128, XW, LDW, (N2 + 7) >> 3, acc);

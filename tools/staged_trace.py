@@ -76,6 +76,9 @@ print("=== replay step B=256: backward kernels of the selected net (stage 0/1 st
 print("  stage0<save>"); dump(t, 0, S0)
 print("  stage1<save>"); dump(t, 32, S1, 40, 96)
 print("  stage2<bwd>"); dump(t, 96, S2, 112, 256)
+v = t[96:110]
+print("   tail backward detail (cycles): d2 %d | d1 %d | dR %d | pool5 bwd %d | conv5^T %d | pool4 bwd + A^T %d | conv4^T + dX2 %d" %
+      (v[8] - v[6], v[9] - v[8], v[10] - v[9], v[11] - v[10], v[12] - v[11], v[13] - v[12], v[7] - v[13]))
 print("  bwd1"); dump(t, 256, B1, 264, 320)
 
 # ---- CUDA-graph timings (no host launch overhead) ----
@@ -106,4 +109,5 @@ for path in ("staged", "fused"):
         with torch.no_grad():
             print(f"[graph] forward B={B} {path}: {graph_time(lambda: net.select_action(b)):.1f} us")
     trn = ReplayTrainer(nets[0], nets[1])
+    trn.overlap = False          # one stream: this tool captures the whole step into its own graph
     print(f"[graph] replay step B=256 {path}: {graph_time(lambda: trn.step(rb)):.1f} us")
