@@ -150,11 +150,19 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
                                     const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
                                     const int32_t *action, const float *reward, const int32_t *index,
                                     const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
-                                    float *loss, float *grad, float *workspace, int phase, void *stream);
+                                    float *loss, float *grad, float *workspace, int phase, uint32_t *tail_sync,
+                                    void *stream);
 /* mdq_qnet_staged_replay_backward differs from mdq_qnet_replay_backward in two ways: the flat gradient's entries of
  * blocks the forward never uses are left untouched (keep a persistent zero-initialised buffer), and `phase` splits the
  * call -- 0: everything; 1: stages 0 / 1 of the selected net only (they do not read q_other, so they may be enqueued on
- * a second stream beside the other net's forward); 2: the remaining launches (same arguments, same workspace). */
+ * a second stream beside the other net's forward); 2: the remaining launches (same arguments, same workspace);
+ * 3: stages 0 / 1 + the tail backward; 4: backward 1 + weight gradients (3 then 4 == 1 then 2 == 0).
+ * tail_sync (phase 3 only, nullable): three zero-initialised device words.  With it the tail kernel may be enqueued BEFORE
+ * q_other has been computed: it runs its forward part and waits, on the device, for one mdq_stream_post(tail_sync, s)
+ * enqueued behind the other net's forward on ANOTHER stream, exactly where the loss first reads q_other (posts and tail
+ * launches pair up one to one, in order).  Never enqueue the post behind the waiting call on the same stream, and not
+ * under a tool that serialises kernels (ncu, compute-sanitizer): the wait traps after ~2 s instead of hanging. */
+int mdq_stream_post(uint32_t *tail_sync, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Layered forward for ONE large graph (a state graph that does not fit the fused kernel's shared memory, e.g. the

@@ -109,7 +109,8 @@ _SIGS = {
     "mdq_qnet_staged_forward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "mdq_qnet_staged_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mdq_qnet_staged_replay_backward": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int,
-                                                _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, c_int, _P]),
+                                                _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, c_int, _P, _P]),
+    "mdq_stream_post": (c_int, [_P, _P]),
     "mdq_qnet_layered_workspace_bytes": (c_int64, [POINTER(mdq_net_t), c_int, c_int]),
     "mdq_qnet_forward_layered": (c_int, [POINTER(mdq_net_t), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),
     "mdq_csr_build": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P]),

@@ -394,7 +394,7 @@ class _FusedQNet(nn.Module):
             ws = self._stg_wss[key] = torch.empty(need, dtype=torch.float32, device=dev)
         return ws
 
-    def _launch_forward(self, x, ei, nptr, eptr, B, max_n, max_e, embedding, want_argmax):
+    def _launch_forward(self, x, ei, nptr, eptr, B, max_n, max_e, embedding, want_argmax, out=None):
         self._ensure_packed()
         if self._flat.device != x.device:
             raise RuntimeError(f"network on {self._flat.device}, data on {x.device}")
@@ -403,7 +403,8 @@ class _FusedQNet(nn.Module):
         if net.in_col0 + net.in_dim > net.x_stride:
             raise ValueError(f"data.x has {net.x_stride} columns, network expects >= {net.in_col0 + net.in_dim}")
         A = net.out_dim
-        out = torch.empty((B, A), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((B, A), dtype=torch.float32, device=x.device)
         emb = torch.empty((B, 2 * net.width), dtype=torch.float32, device=x.device) if embedding else None
         am = torch.empty((B,), dtype=torch.int32, device=x.device) if want_argmax else None
         E = int(ei.shape[1])
@@ -457,7 +458,7 @@ class _FusedQNet(nn.Module):
         _lib.check(rc, "mdq_qnet_backward")
 
     def _launch_replay_backward(self, x, ei, nptr, eptr, B, max_n, max_e, mode, action, reward, index, next_slot, q_other,
-                                batch, gamma, scalar, loss, flat_grad, phase=0):
+                                batch, gamma, scalar, loss, flat_grad, phase=0, sync=None):
         self._ensure_packed()
         net = self._net
         net.x_stride = int(x.shape[1])
@@ -472,9 +473,11 @@ class _FusedQNet(nn.Module):
                                                        _lib.ptr(action), _lib.ptr(reward), _lib.ptr(index),
                                                        _lib.ptr(next_slot), _lib.ptr(q_other), int(batch), float(gamma),
                                                        _lib.ptr(scalar), _lib.ptr(loss), _lib.ptr(flat_grad), _lib.ptr(ws),
-                                                       int(phase), _lib.stream_ptr())
+                                                       int(phase), _lib.ptr(sync), _lib.stream_ptr())
             _lib.check(rc, "mdq_qnet_staged_replay_backward")
             return
+        if phase in (3, 4) or sync is not None:
+            raise RuntimeError("phases 3 / 4 (early tail launch) exist on the staged path only")
         if phase == 1:
             return      # the fused kernel has no split: everything happens in the finishing call
         if ei.dtype != torch.int64:

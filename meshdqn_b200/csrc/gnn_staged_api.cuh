@@ -202,12 +202,15 @@ int stg_launch_tail(stg::TArgs &a, const StgGeom &G, cudaStream_t st)
 }
 
 // phase 0: everything; 1: stages 0 / 1 only (independent of Q_other: may run beside the other net's forward);
-// 2: the rest (tail backward, backward 1, weight gradients).  zero_grad: memset the flat gradient first (the unused
+// 2: the rest (tail backward, backward 1, weight gradients); 3: stages 0 / 1 + tail backward (with `sync`: launched before
+// Q_other exists, the tail waits for mdq_stream_post where the loss needs it); 4: backward 1 + weight gradients.  zero_grad: memset the flat gradient first (the unused
 // blocks' entries); the replay path keeps a persistent, pre-zeroed gradient buffer instead.
 struct StgLoss { int batch; const int32_t *next_slot; float *loss; };
 int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArgs &a2, float *grad, float *workspace,
-                        cudaStream_t st, int phase, bool zero_grad, const StgLoss &ls)
+                        cudaStream_t st, int phase, bool zero_grad, const StgLoss &ls, unsigned *sync = nullptr)
 {
+    const bool do_stages = phase == 0 || phase == 1 || phase == 3, do_tail = phase == 0 || phase == 2 || phase == 3;
+    const bool do_rest = phase == 0 || phase == 2 || phase == 4;
     const mdq_net_t &net = *c.net;
     if (!stg::supported(net, max_n, max_e)) { mdq::set_error("staged path: unsupported network / graph size"); return MDQ_EINVAL; }
     stg::Plan P;
@@ -235,17 +238,17 @@ int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArg
     StgWs w;
     stg_carve(G, workspace + ((fused_ws + 3) & ~(int64_t)3), true, w);
     float *ws = workspace;
-    if (zero_grad && phase != 2) {
+    if (zero_grad && do_stages) {
         cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)net.n_params * sizeof(float), st);
         if (e != cudaSuccess) { mdq::set_error("memset grad: %s", cudaGetErrorString(e)); return MDQ_ECUDA; }
     }
     float *x2 = ws + wd.l[2].i_off, *x3 = ws + wd.l[3].i_off;
     int rc = MDQ_OK;
-    if (phase != 2) {
+    if (do_stages) {
         rc = stg_launch_01<true>(c, G, P, w, ws + wd.l[0].i_off, ws + wd.l[1].i_off, x2, st);
         if (rc != MDQ_OK || phase == 1) return rc;
     }
-    {
+    if (do_tail) {
         stg::TArgs keep = a2;   // the caller filled the loss-gradient fields
         stg_tail_common(a2, c, G, P, w, x2, x3, true);
         a2.mode = keep.mode; a2.gout = keep.gout; a2.rp_action = keep.rp_action; a2.rp_reward = keep.rp_reward;
@@ -257,8 +260,10 @@ int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArg
         a2.pool4_d = ws + wd.l[nb + 2].d_off; a2.pool5_d = ws + wd.l[nb + 3].d_off;
         a2.bias4_d = ws + wd.l[2 * nb + 3 + 2].d_off; a2.bias5_d = ws + wd.l[2 * nb + 3 + 3].d_off;
         a2.dX2 = w.dX2; a2.dR = w.dR;
+        a2.sync = sync;
         if ((rc = stg_launch_tail<true>(a2, G, st)) != MDQ_OK) return rc;
     }
+    if (!do_rest) return MDQ_OK;
     {
         stg::B1Args a;
         memset(&a, 0, sizeof(a));
@@ -379,11 +384,11 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
                                     const int32_t *edge_ptr, int n_graphs, int max_n, int max_e, int mode,
                                     const int32_t *action, const float *reward, const int32_t *index,
                                     const int32_t *next_slot, const float *q_other, int batch, float gamma, float *scalar,
-                                    float *loss, float *grad, float *workspace, int phase, void *stream)
+                                    float *loss, float *grad, float *workspace, int phase, uint32_t *tail_sync, void *stream)
 {
     if (!net || !params || !wsplit || !x || !grad || !workspace || !action || !reward || !index || !next_slot || !scalar ||
         !loss || n_graphs < 1 || batch < 1 || (mode != 1 && mode != 2) || (mode == 2 && phase != 1 && !q_other) ||
-        phase < 0 || phase > 2 || (reinterpret_cast<uintptr_t>(workspace) & 15)) {
+        phase < 0 || phase > 4 || (tail_sync && phase != 3) || (reinterpret_cast<uintptr_t>(workspace) & 15)) {
         mdq::set_error("mdq_qnet_staged_replay_backward: bad argument");
         return MDQ_EINVAL;
     }
@@ -393,7 +398,14 @@ int mdq_qnet_staged_replay_backward(const mdq_net_t *net, const float *params, c
     a2.mode = mode; a2.rp_action = action; a2.rp_reward = reward; a2.rp_index = index; a2.rp_qother = q_other;
     a2.rp_gamma = gamma; a2.rp_inv_batch = 1.f / (float)batch; a2.rp_scalar = scalar;
     return stg_backward_launch(c, n_graphs, max_n, max_e, a2, grad, workspace, (cudaStream_t)stream, phase, false,
-                               StgLoss{batch, next_slot, loss});
+                               StgLoss{batch, next_slot, loss}, tail_sync);
+}
+
+int mdq_stream_post(uint32_t *sync, void *stream)
+{
+    if (!sync) { mdq::set_error("mdq_stream_post: null argument"); return MDQ_EINVAL; }
+    stg::k_post<<<1, 1, 0, (cudaStream_t)stream>>>(sync);
+    return mdq::check_launch("k_post");
 }
 
 }  // extern "C"

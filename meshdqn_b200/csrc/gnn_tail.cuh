@@ -86,6 +86,17 @@ struct Ring {
 // keep the ring full (wait for a stage to come back, start its bulk copy); the compute warps never issue a copy and
 // synchronise among themselves on a named barrier.
 constexpr int NTH_TAIL = NTH + 32;
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void k_post(unsigned *sync)
+{
+    __threadfence();
+    atomicAdd(sync, 1u);
+}
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); }
 
 // out[r][c] = sum_k act[r][k] * W[k][c] for a weight matrix of K rows (multiple of 32 rows per block, last block may be
@@ -167,6 +178,9 @@ struct TArgs {
     float *lin_in[3], *lin_d[3];  // weight-gradient rows: inputs Rs / y1 / y2, deltas d1 / d2 / d3
     float *c5_d, *c4_d, *pool4_d, *pool5_d, *bias4_d, *bias5_d;
     float *dX2, *dR;              // [B][R2][128], [B][256]
+    // early launch (BWD, modes 1 / 2): the kernel is started BEFORE Q_other exists and waits for it right where the loss needs
+    // it -- sync[0] = posts (k_post after the other net's forward), sync[1] = tail launches completed, sync[2] = CTA ticket
+    unsigned *sync;
     int o_ring, o_x2s, o_xw, o_x3s, o_h4, o_rs, o_y1, o_y2, o_y3, o_es, o_int, o_f, o_rowg, o_lg, total;
 };
 
@@ -251,8 +265,9 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
     for (int gi = 0; gi < ng; ++gi)
         for (int j = tid; j < ecnt[gi]; j += NTH) es2[gi * a.EC2 + j] = a.e2[(size_t)(g0 + gi) * a.EC2 + j];
     float *lgf = reinterpret_cast<float *>(sm + a.o_lg);   // [GS][4]: sel (as int bits), pred, nsv, rew
-    if (BWD && a.mode != 0) {
-        // the transition data and Q_other row of each graph: fetched now so that their (cold) latency hides under the forward chain
+    // the transition data and Q_other row of each graph.  Normally fetched now, so that their (cold) latency hides under the
+    // forward chain; an early-launched kernel (a.sync) fetches them after its wait instead, with L2-coherent loads
+    auto fetch_loss_inputs = [&](bool coherent) {
         for (int gi = warp; gi < ng; gi += NTH / 32) {
             const int g = g0 + gi;
             int sel = 0;
@@ -264,14 +279,15 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
                 float m = -INFINITY;
                 if (slot >= 0) {
                     const float *q = a.rp_qother + (size_t)slot * A;
-                    for (int c = lane; c < A; c += 32) m = fmaxf(m, __ldg(q + c));
+                    for (int c = lane; c < A; c += 32) m = fmaxf(m, coherent ? __ldcg(q + c) : __ldg(q + c));
 #pragma unroll
                     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
                 }
                 nsv = slot >= 0 ? m : 0.f;
             } else {
                 const int b = a.rp_index[g];
-                pred = __ldg(a.rp_qother + (size_t)b * A + a.rp_action[b]);
+                const float *q = a.rp_qother + (size_t)b * A + a.rp_action[b];
+                pred = coherent ? __ldcg(q) : __ldg(q);
                 rew = a.rp_reward[b];
             }
             if (lane == 0) {
@@ -281,6 +297,11 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
                 lgf[gi * 4 + 3] = rew;
             }
         }
+    };
+    unsigned expected = 0;
+    if (BWD && a.mode != 0) {
+        if (a.sync) expected = *reinterpret_cast<volatile unsigned *>(a.sync + 1) + 1u;   // same value in every CTA (see the end)
+        else fetch_loss_inputs(false);
     }
     cta_sync();
     STG_TRACE(a.trace, 96, 2);   // inputs loaded
@@ -418,6 +439,19 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
     }
     cta_sync();
     STG_TRACE(a.trace, 96, 5);   // MLP
+    if (BWD && a.mode != 0 && a.sync) {
+        // Q_other is being computed by the other net's forward on another stream: wait for its post, then fetch
+        if (tid == 0) {
+            unsigned spins = 0;
+            while ((int)(ld_acquire_gpu(a.sync) - expected) < 0) {
+                __nanosleep(100);
+                if (++spins > (1u << 24)) __trap();      // a post that never comes must fail loudly, not hang the device
+            }
+        }
+        cta_sync();
+        fetch_loss_inputs(true);
+        cta_sync();
+    }
     // ---- softmax, argmax (first maximum) ----
     for (int gi = warp; gi < ng; gi += NTH / 32) {
         float *y = y3 + gi * LDY3;
@@ -624,6 +658,18 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
         }
     }
     STG_TRACE(a.trace, 96, 7);   // end
+    if (BWD && a.mode != 0 && a.sync) {
+        // the last CTA to finish counts this launch as completed; every CTA read sync[1] at its start, before any could finish last
+        cta_sync();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(a.sync + 2, 1u) == gridDim.x - 1) {
+                a.sync[2] = 0u;
+                __threadfence();
+                atomicAdd(a.sync + 1, 1u);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -22,6 +22,8 @@ ONE all-reduce (sum) of the flat fp32 gradient (the first ``n_used`` floats of t
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -281,6 +283,13 @@ class ReplayTrainer:
         self.overlap = True  # segments on three streams (see "one replay step" below); False: everything on the current one
         self._side = None
         self._upd = None
+        # early tail launch: the selected net's tail kernel joins segment H and waits ON THE DEVICE for Q_other (a post
+        # enqueued behind the other net's forward), instead of the whole segment T waiting for segment A on the host's
+        # stream order -- its forward half (~25 us) then runs beside A.  Off under tools that serialise kernels (the post
+        # could never run while the tail waits): ncu / compute-sanitizer inject themselves through CUDA_INJECTION64_PATH.
+        self.early_tail = not any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                                                            "MDQ_NO_EARLY_TAIL"))
+        self._sync = None
         # graphs=True: the launches of a step (everything but the NCCL all-reduce) are captured once per (select branch,
         # minibatch buffers) and replayed -- the ~13 launches cost ~200 us of host time per step otherwise, more than
         # the kernels.  Needs minibatches at fixed device addresses (the same ReplayBatch, or DevicePrefetcher(static=True)).
@@ -367,17 +376,37 @@ class ReplayTrainer:
             return sel, s_args, 1, batch.next_slot, net2, n_args
         return sel, n_args, 2, batch.owner, net1, s_args
 
-    def _seg_H(self, batch, r, scalar, loss):
+    def _seg_H(self, batch, r, scalar, loss, q_other=None, sync=None):
+        """Stages 0 / 1 of the selected net; with ``sync`` also its tail kernel, which waits for ``q_other`` on the device."""
         sel, args, mode, index, other, o_args = r
         st = self._adam_state(sel)
-        self.nets[sel]._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, None,
-                                               int(batch.actions.shape[0]), self.gamma, scalar, loss, st["g"], phase=1)
+        self.nets[sel]._launch_replay_backward(*args, mode, batch.actions, batch.rewards, index, batch.next_slot, q_other,
+                                               int(batch.actions.shape[0]), self.gamma, scalar, loss, st["g"],
+                                               phase=1 if sync is None else 3, sync=sync)
 
-    def _seg_A(self, r):
+    def _seg_A(self, r, out=None, sync=None):
         other, o_args = r[4], r[5]
         if o_args is None:
             return None
-        return other._launch_forward(*o_args, False, False)[0]
+        q = other._launch_forward(*o_args, False, False, out=out)[0]
+        if sync is not None:
+            with torch.cuda.device(q.device):
+                _lib.check(_lib.lib().mdq_stream_post(_lib.ptr(sync), _lib.stream_ptr()), "mdq_stream_post")
+        return q
+
+    def _early(self, r, dev):
+        """The tail may be launched early when both halves exist: a forward of the other net to wait for, and a selected
+        net on the staged path (the fused kernel has no split)."""
+        sel, args, mode, index, other, o_args = r
+        if not self.early_tail or o_args is None:
+            return None
+        self.nets[sel]._ensure_packed()
+        other._ensure_packed()
+        if not self.nets[sel]._use_staged(int(args[5]), int(args[6])):
+            return None
+        if self._sync is None or self._sync.device != dev:
+            self._sync = torch.zeros(4, dtype=torch.int32, device=dev)
+        return self._sync
 
     def _seg_T(self, batch, r, q_other, scalar, loss, phase):
         sel, args, mode, index, other, o_args = r
@@ -452,31 +481,41 @@ class ReplayTrainer:
                         self._seen.clear()
                     self._seen.add(key)
         pend_net, pend_other = net.__dict__.get("_pending"), other.__dict__.get("_pending")
-        # H on the side stream: after the inputs (main) and the selected net's previous update
-        side.wait_stream(main)
-        if pend_net is not None:
-            side.wait_event(pend_net)
+        sync = q_buf = None
         if entry is None:
             scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
-        with torch.cuda.stream(side):
-            if entry is not None:
-                entry["H"].replay()
-            else:
-                self._seg_H(batch, r, scalar, loss)
-        # A on the main stream: only a freshly de-selected net still has an update in flight
+            sync = self._early(r, dev)
+            if sync is not None:
+                q_buf = torch.empty((int(o_args[4]), other._net.out_dim), dtype=torch.float32, device=dev)
+        inputs_ready = torch.cuda.Event()
+        inputs_ready.record(main)
+        # A is ENQUEUED first (main stream; only a freshly de-selected net still has an update in flight).  An early-launched
+        # tail waits on the device for A's post: with A already in the queue nothing the host does afterwards -- a first-use
+        # cudaMalloc that synchronises the device, an exception -- can keep that post from arriving.
         if pend_other is not None:
             main.wait_event(pend_other)
         if entry is not None:
             entry["A"].replay()
         else:
-            q_other = self._seg_A(r)
+            q_other = self._seg_A(r, q_buf, sync)
+        # H on the side stream: after the inputs and the selected net's previous update, beside A
+        side.wait_event(inputs_ready)
+        if pend_net is not None:
+            side.wait_event(pend_net)
+        with torch.cuda.stream(side):
+            if entry is not None:
+                entry["H"].replay()
+            else:
+                self._seg_H(batch, r, scalar, loss, q_buf, sync)
+                if q_buf is not None:
+                    q_buf.record_stream(side)
         main.wait_stream(side)
         if entry is not None:
             entry["T"].replay()
             loss = entry["loss"]
         else:
-            self._seg_T(batch, r, q_other, scalar, loss, 2)
+            self._seg_T(batch, r, q_other, scalar, loss, 2 if sync is None else 4)
         # U on the update stream
         ev = torch.cuda.Event()
         ev.record(main)
@@ -517,6 +556,11 @@ class ReplayTrainer:
         scalar = torch.empty(int(args[4]), dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         entry = {"batch": batch, "loss": loss, "scalar": scalar}
+        sync = self._early(r, dev)
+        q_buf = None
+        if sync is not None:
+            q_buf = torch.empty((int(o_args[4]), other._net.out_dim), dtype=torch.float32, device=dev)
+        entry["q_other"] = q_buf
         L = _lib.lib()
         n0 = int(L.mdq_launch_count())
         pool = torch.cuda.graph_pool_handle()
@@ -524,11 +568,11 @@ class ReplayTrainer:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 if name == "H":
-                    self._seg_H(batch, r, scalar, loss)
+                    self._seg_H(batch, r, scalar, loss, q_buf, sync)
                 elif name == "A":
-                    entry["q_other"] = self._seg_A(r)
+                    entry["q_other"] = self._seg_A(r, q_buf, sync)
                 elif name == "T":
-                    self._seg_T(batch, r, entry["q_other"], scalar, loss, 2)
+                    self._seg_T(batch, r, entry["q_other"], scalar, loss, 2 if sync is None else 4)
                 else:
                     self._seg_U(sel)
             entry[name] = g
