@@ -195,6 +195,16 @@ __global__ void __launch_bounds__(256) k_wsplit(const Plan P, const float *__res
         if ((buf) && blockIdx.x == 0 && threadIdx.x == 0) (buf)[(base) + (i)] = clock64(); \
     } while (0)
 
+// wall-clock (%globaltimer, ns) stamps of CTA 0 at slot 400 + i: a cross-kernel, cross-stream timeline of one step
+#define STG_GT(buf, i)                                                                                     \
+    do {                                                                                                   \
+        if ((buf) && blockIdx.x == 0 && threadIdx.x == 0) {                                                \
+            long long t_;                                                                                  \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                          \
+            (buf)[400 + (i)] = t_;                                                                         \
+        }                                                                                                  \
+    } while (0)
+
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))); }
 
@@ -269,6 +279,7 @@ __global__ void __launch_bounds__(NTH, 2) k_stage0(const __grid_constant__ S0Arg
     unsigned long long *k64 = reinterpret_cast<unsigned long long *>(sm + a.o_k64);
 
     STG_TRACE(a.trace, 0, 0);
+    STG_GT(a.trace, SAVE ? 2 : 0);
     const int nb0 = a.nptr[g], n = a.nptr[g + 1] - nb0;
     const int eb0 = a.eptr[g], E = a.eptr[g + 1] - eb0;
     if (tid == 0) {
@@ -574,6 +585,7 @@ __global__ void __launch_bounds__(NTH, 2) k_stage0(const __grid_constant__ S0Arg
     }
     __syncthreads();
     STG_TRACE(a.trace, 0, 13);  // outputs written
+    STG_GT(a.trace, SAVE ? 3 : 1);
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
@@ -884,6 +896,7 @@ __global__ void __launch_bounds__(NTH, 1) k_stage1(const __grid_constant__ S1Arg
     p.sta = a.sta; p.stb = 2; p.wsplit = a.wsplit; p.blk = a.blk; p.nblk = a.nblk;
     p.j = 0; p.nissued = 0; p.acc_cnt = 0; p.trace = a.trace; p.tpos = 32 + 8; p.tend = 96;
     STG_TRACE(a.trace, 32, 0);
+    STG_GT(a.trace, SAVE ? 6 : 4);
     if (tid == 0) {
         p.init_barriers();
         int r = 0, o2 = 0;
@@ -1066,6 +1079,7 @@ __global__ void __launch_bounds__(NTH, 1) k_stage1(const __grid_constant__ S1Arg
     }
     __syncthreads();
     STG_TRACE(a.trace, 32, 5);   // outputs
+    STG_GT(a.trace, SAVE ? 7 : 5);
     if (warp == 1) tmem_dealloc(p.tmem, (unsigned)a.tmem_cols);
 }
 

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
     rg.full = bars; rg.empty = bars + 8; rg.base = sm + a.o_ring; rg.params = P; rg.wsplit = a.wsplit; rg.blk = a.blk; rg.nblk = a.nblk;
     rg.j = 0; rg.nissued = 0;
     STG_TRACE(a.trace, 96, 0);
+    STG_GT(a.trace, BWD ? 10 : 8);
     if (tid == 0) rg.init();
     __syncthreads();               // all NTH_TAIL threads: the barriers exist
     if (tid >= NTH) {              // producer warp
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
     STG_TRACE(a.trace, 96, 5);   // MLP
     if (BWD && a.mode != 0 && a.sync) {
         // Q_other is being computed by the other net's forward on another stream: wait for its post, then fetch
+        STG_GT(a.trace, 12);
         if (tid == 0) {
             unsigned spins = 0;
             while ((int)(ld_acquire_gpu(a.sync) - expected) < 0) {
@@ -449,6 +451,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
             }
         }
         cta_sync();
+        STG_GT(a.trace, 13);
         fetch_loss_inputs(true);
         cta_sync();
     }
@@ -658,6 +661,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_tail(const __grid_constant__ TA
         }
     }
     STG_TRACE(a.trace, 96, 7);   // end
+    STG_GT(a.trace, BWD ? 11 : 9);
     if (BWD && a.mode != 0 && a.sync) {
         // the last CTA to finish counts this launch as completed; every CTA read sync[1] at its start, before any could finish last
         cta_sync();
@@ -744,6 +748,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_bwd1(const __grid_constant__ B1
     rg.full = bars; rg.empty = bars + 8; rg.base = sm + a.o_ring; rg.params = P; rg.wsplit = a.wsplit; rg.blk = a.blk; rg.nblk = a.nblk;
     rg.j = 0; rg.nissued = 0;
     STG_TRACE(a.trace, 256, 0);
+    STG_GT(a.trace, 14);
     if (tid == 0) rg.init();
     __syncthreads();               // all NTH_TAIL threads: the barriers exist
     if (tid >= NTH) {              // producer warp
@@ -954,6 +959,7 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_bwd1(const __grid_constant__ B1
         if (tid == 0) *a.loss = red[0] / (float)a.batch;
     }
     STG_TRACE(a.trace, 256, 5);  // end
+    STG_GT(a.trace, 15);
 }
 
 }  // namespace stg

@@ -283,12 +283,15 @@ class ReplayTrainer:
         self.overlap = True  # segments on three streams (see "one replay step" below); False: everything on the current one
         self._side = None
         self._upd = None
-        # early tail launch: the selected net's tail kernel joins segment H and waits ON THE DEVICE for Q_other (a post
-        # enqueued behind the other net's forward), instead of the whole segment T waiting for segment A on the host's
-        # stream order -- its forward half (~25 us) then runs beside A.  Off under tools that serialise kernels (the post
-        # could never run while the tail waits): ncu / compute-sanitizer inject themselves through CUDA_INJECTION64_PATH.
-        self.early_tail = not any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
-                                                            "MDQ_NO_EARLY_TAIL"))
+        # early tail launch (opt-in, MDQ_EARLY_TAIL=1 or trainer.early_tail = True): the selected net's tail kernel joins
+        # segment H and waits ON THE DEVICE for Q_other (a post enqueued behind the other net's forward) instead of the whole
+        # segment T waiting for segment A.  Built to take the tail's forward half (~25 us) off the critical path; measured,
+        # it buys nothing -- tools/step_timeline.py shows the two tail kernels slowing each other down when they co-run
+        # (23 -> 37 us and 56 -> 70 us): the step is bound by the machine's total issue capacity, not by the dependency
+        # chain.  Never on under tools that serialise kernels (ncu, compute-sanitizer: the post could not run
+        # while the tail waits; they inject themselves through CUDA_INJECTION64_PATH).
+        self.early_tail = os.environ.get("MDQ_EARLY_TAIL") == "1" and not any(
+            k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR"))
         self._sync = None
         # graphs=True: the launches of a step (everything but the NCCL all-reduce) are captured once per (select branch,
         # minibatch buffers) and replayed -- the ~13 launches cost ~200 us of host time per step otherwise, more than
@@ -490,26 +493,37 @@ class ReplayTrainer:
                 q_buf = torch.empty((int(o_args[4]), other._net.out_dim), dtype=torch.float32, device=dev)
         inputs_ready = torch.cuda.Event()
         inputs_ready.record(main)
-        # A is ENQUEUED first (main stream; only a freshly de-selected net still has an update in flight).  An early-launched
-        # tail waits on the device for A's post: with A already in the queue nothing the host does afterwards -- a first-use
-        # cudaMalloc that synchronises the device, an exception -- can keep that post from arriving.
-        if pend_other is not None:
-            main.wait_event(pend_other)
-        if entry is not None:
-            entry["A"].replay()
-        else:
-            q_other = self._seg_A(r, q_buf, sync)
-        # H on the side stream: after the inputs and the selected net's previous update, beside A
-        side.wait_event(inputs_ready)
-        if pend_net is not None:
-            side.wait_event(pend_net)
-        with torch.cuda.stream(side):
+
+        def run_A():      # main stream; only a freshly de-selected net still has an update in flight
+            if pend_other is not None:
+                main.wait_event(pend_other)
             if entry is not None:
-                entry["H"].replay()
-            else:
-                self._seg_H(batch, r, scalar, loss, q_buf, sync)
-                if q_buf is not None:
-                    q_buf.record_stream(side)
+                entry["A"].replay()
+                return entry["q_other"]
+            return self._seg_A(r, q_buf, sync)
+
+        def run_H():      # side stream: after the inputs and the selected net's previous update, beside A
+            side.wait_event(inputs_ready)
+            if pend_net is not None:
+                side.wait_event(pend_net)
+            with torch.cuda.stream(side):
+                if entry is not None:
+                    entry["H"].replay()
+                else:
+                    self._seg_H(batch, r, scalar, loss, q_buf, sync)
+                    if q_buf is not None:
+                        q_buf.record_stream(side)
+
+        # Queue order.  An early-launched tail (in H) waits on the device for A's post.  Replaying graphs, the host does
+        # nothing between the two replays, and H goes first so that its tail starts as early as possible (it is the long
+        # pole: stage 0 -> stage 1 -> tail).  Launching kernel by kernel, A goes first: whatever the host does afterwards --
+        # a first-use cudaMalloc that synchronises the device, an exception -- the post is already in the queue.
+        if entry is not None:
+            run_H()
+            q_other = run_A()
+        else:
+            q_other = run_A()
+            run_H()
         main.wait_stream(side)
         if entry is not None:
             entry["T"].replay()

@@ -173,13 +173,16 @@ def test_replay_steps_staged_equals_fused(cuda_device):
         trans.append((s, int(torch.randint(0, 181, (1,), generator=g)), nx, float(torch.randn(1, generator=g))))
     rb = ReplayBatch.from_transitions(trans).to(cuda_device)
     out = {}
-    for name, path, overlap in (("staged", "staged", True), ("staged_serial", "staged", False), ("fused", "fused", False)):
+    for name, path, overlap in (("staged", "staged", True), ("staged_serial", "staged", False), ("fused", "fused", False),
+                                ("staged_early", "staged", True)):
         nets = [make(cuda_device, True, path)[0] for _ in range(2)]
         tr = ReplayTrainer(nets[0], nets[1], lr=1e-3, weight_decay=1e-6, gamma=1.0, target_update=2)
         tr.overlap = overlap
+        tr.early_tail = name == "staged_early"      # the tail launched before Q_other exists, waiting for it on the device
         losses = [float(tr.step(rb)) for _ in range(4)]
         out[name] = (losses, nets[0]._flat.clone(), nets[1]._flat.clone())
-    assert out["staged"][0] == out["staged_serial"][0]                      # the side stream changes nothing
+    assert out["staged"][0] == out["staged_serial"][0] == out["staged_early"][0]   # neither the side stream nor the early tail changes a bit
+    assert torch.equal(out["staged"][1], out["staged_early"][1]) and torch.equal(out["staged"][2], out["staged_early"][2])
     assert torch.equal(out["staged"][1], out["staged_serial"][1]) and torch.equal(out["staged"][2], out["staged_serial"][2])
     for a, b_ in zip(out["staged"][0], out["fused"][0]):
         assert abs(a - b_) <= 1e-5 * max(1.0, abs(b_))
