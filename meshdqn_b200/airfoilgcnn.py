@@ -584,6 +584,11 @@ class _FusedQNet(nn.Module):
             out, emb, _ = self._launch_forward_layered(x, ei, embedding, False)
             return emb if embedding else out
         params = [p for _, p in self._entries]
+        if not embedding:
+            # through the dispatcher: torch.ops.meshdqn_b200.qnet_forward (ops.py) -- the same launch, with its autograd
+            # formula (mdq_qnet_backward) and a fake implementation for tracing
+            from . import ops
+            return torch.ops.meshdqn_b200.qnet_forward(params, x, ei, nptr, eptr, ops.net_handle(self), B, max_n, max_e)
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _QNetFunction.apply(self, x, ei, nptr, eptr, B, max_n, max_e, embedding, *params)
         out, emb, _ = self._launch_forward(x, ei, nptr, eptr, B, max_n, max_e, embedding, False)
@@ -598,8 +603,8 @@ class _FusedQNet(nn.Module):
         if self._use_layered(B, max_n, max_e):
             out, _, am = self._launch_forward_layered(x, ei, False, True)
             return am, out
-        out, _, am = self._launch_forward(x, ei, nptr, eptr, B, max_n, max_e, False, True)
-        return am, out
+        from . import ops
+        return torch.ops.meshdqn_b200.qnet_select_action(x, ei, nptr, eptr, ops.net_handle(self), B, max_n, max_e)
 
 
 class NodeRemovalNet(_FusedQNet):

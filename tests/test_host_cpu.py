@@ -343,3 +343,34 @@ def test_env_workers_step_in_replica_order():
             w.step_all([0, -1, 0, 0])
     finally:
         w.close()
+
+
+def test_torch_library_ops_are_registered_with_fake_kernels():
+    """ops.py: the hot-path entry points live under torch.ops.meshdqn_b200 with schemas and fake (meta) kernels, so a traced
+    program sees opaque ops of known output shape; there is no CPU kernel behind them."""
+    import pytest
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from meshdqn_b200 import ops
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    names = {"qnet_forward", "qnet_backward", "qnet_select_action", "mesh_smooth", "polygon_distance", "drag_lift"}
+    assert names <= set(dir(torch.ops.meshdqn_b200))
+    assert "Tensor[] params" in str(torch.ops.meshdqn_b200.qnet_forward.default._schema)
+    net = NodeRemovalNet(181, 128, 0.1)
+    net.set_num_nodes(17)
+    h = ops.net_handle(net)
+    assert ops.net_handle(net) == h
+    with FakeTensorMode():
+        x = torch.empty(360, 17, device="cuda")
+        ei = torch.empty(2, 700, dtype=torch.int64, device="cuda")
+        nptr = torch.empty(3, dtype=torch.int32, device="cuda")
+        q = torch.ops.meshdqn_b200.qnet_forward([], x, ei, nptr, nptr, h, 2, 180, 350)
+        am, q2 = torch.ops.meshdqn_b200.qnet_select_action(x, ei, nptr, nptr, h, 2, 180, 350)
+        c = torch.empty(50, 2, dtype=torch.float64, device="cuda")
+        d = torch.ops.meshdqn_b200.polygon_distance(c, torch.empty(7, dtype=torch.int32, device="cuda"), c[:5])
+        dl = torch.ops.meshdqn_b200.drag_lift(c, nptr, nptr, nptr, nptr, torch.empty(5, 80, 2, dtype=torch.float64, device="cuda"),
+                                             torch.empty(5, 50, dtype=torch.float64, device="cuda"), 1e-3, 30)
+    assert q.shape == (2, 181) and am.shape == (2,) and am.dtype == torch.int32 and q2.shape == (2, 181)
+    assert d.shape == (7,) and d.dtype == torch.float64 and dl.shape == (2, 5)
+    with pytest.raises(NotImplementedError):
+        torch.ops.meshdqn_b200.polygon_distance(torch.zeros(4, 2, dtype=torch.float64), torch.zeros(2, dtype=torch.int32),
+                                                torch.zeros(3, 2, dtype=torch.float64))

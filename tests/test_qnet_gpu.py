@@ -192,3 +192,41 @@ def test_too_large_graph_fails_loudly(cuda_device):
             net(b.to(cuda_device))
     with pytest.raises(NotImplementedError):          # the layered path is forward-only
         net(rand_graph(g, n=4000, e=8000).to(cuda_device))
+
+
+def test_torch_ops_layer(cuda_device):
+    """torch.ops.meshdqn_b200.*: the module's forward IS the registered op (same numbers), autograd flows through the op's
+    registered formula to the PyG-shaped parameters, and torch.library.opcheck accepts the registrations."""
+    from meshdqn_b200 import ops
+    net, ref = make_nets(cuda_device, lively=True)
+    g = torch.Generator().manual_seed(23)
+    b = Batch.from_data_list([rand_graph(g) for _ in range(6)]).to(cuda_device)
+    x, ei, nptr, eptr, B, max_n, max_e = net._prep(b)
+    net._ensure_packed()
+    h = ops.net_handle(net)
+    params = [p for _, p in net._entries]
+    with torch.no_grad():
+        q_mod = net(b)
+        q_op = torch.ops.meshdqn_b200.qnet_forward(params, x, ei, nptr, eptr, h, B, max_n, max_e)
+        am, q_sel = torch.ops.meshdqn_b200.qnet_select_action(x, ei, nptr, eptr, h, B, max_n, max_e)
+    assert torch.equal(q_mod, q_op) and torch.equal(q_sel, q_op) and torch.equal(am.long(), q_op.argmax(1))
+    # autograd through the op's registered formula == through the module (which test_backward_matches_autograd_oracle pins
+    # against the oracle): bit-identical parameter gradients
+    w = torch.randn(6, 181, generator=g).to(cuda_device)
+    (torch.ops.meshdqn_b200.qnet_forward(params, x, ei, nptr, eptr, h, B, max_n, max_e) * w).sum().backward()
+    g_op = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad()
+    (net(b) * w).sum().backward()
+    g_mod = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    assert len(g_op) >= 14 and g_op.keys() == g_mod.keys()
+    assert all(torch.equal(g_op[k], g_mod[k]) for k in g_op)
+    torch.library.opcheck(torch.ops.meshdqn_b200.qnet_select_action.default, (x, ei, nptr, eptr, h, B, max_n, max_e),
+                          test_utils=("test_schema", "test_faketensor"))
+    coords = torch.rand(64, 2, dtype=torch.float64, device=cuda_device)
+    ring = torch.tensor([[0.2, 0.2], [0.8, 0.2], [0.8, 0.8], [0.2, 0.8]], dtype=torch.float64, device=cuda_device)
+    idx = torch.arange(0, 64, 3, dtype=torch.int32, device=cuda_device)
+    torch.library.opcheck(torch.ops.meshdqn_b200.polygon_distance.default, (coords, idx, ring),
+                          test_utils=("test_schema", "test_faketensor"))
+    d = torch.ops.meshdqn_b200.polygon_distance(coords, idx, ring)
+    inside = ((coords[idx.long()] > 0.2) & (coords[idx.long()] < 0.8)).all(1)
+    assert torch.equal(d == 0, inside)
