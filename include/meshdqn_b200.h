@@ -360,6 +360,19 @@ int mdq_drag_lift(const double *coords, const int32_t *cells, const int32_t *cel
                   const int32_t *tags, const int32_t *edge_cell, int T, const double *U, const double *P, double mu,
                   double *drag_lift, void *stream);
 
+/* mdq_interpolate followed by mdq_drag_lift on the TARGET mesh in the same two launches: the last block of the miss pass
+ * integrates the airfoil facets (tags == 1) over the freshly interpolated U / P -- "interpolation ... followed by a fused
+ * surface-integral drag/lift reduction".  Same reduction shape as mdq_drag_lift: bit-identical drag / lift.
+ *   cells, cell_edges, tags, edge_cell: of the target mesh (mdq_mesh_topology / mdq_mesh_tags_removable);
+ *   ticket: one device uint32, zero before the first call (left zero by every call). */
+int mdq_interpolate_drag_lift(const double *coords, int nv, const int32_t *edges, int ne, const double *coords0,
+                              const int32_t *cells0, const int32_t *cell_edges0, int nv0, int ne0, int nc0,
+                              const double *h_grid, const int32_t *bin_ptr, const int32_t *bin_cells, double tol, int T,
+                              const double *U0, const double *P0, double *U, double *P, int32_t *cell_of,
+                              int32_t *miss_count, int32_t *miss_list, const int32_t *cells, const int32_t *cell_edges,
+                              const int32_t *tags, const int32_t *edge_cell, double mu, double *drag_lift, uint32_t *ticket,
+                              void *stream);
+
 /* Env2DAirfoil.get_state (Env2DAirfoil.py:244-315) on device, quirks B1-B3 included:
  *   dist [nrem] f64 distances of the removable vertices (list order), removable_idx [nrem] i32;
  *   picks order[offset : offset+N] of the stable ascending argsort -> n_closest [N] (positions in the

@@ -69,6 +69,7 @@ class SourceField:
         self.micro_bins_per_cell = float(micro_bins_per_cell)
         self.bucket_factor = int(bucket_factor)
         self.tile = None
+        self._ticket = None
         d = mesh.device
         self.U0 = torch.as_tensor(np.ascontiguousarray(U0, dtype=np.float64)).to(d).contiguous()
         self.P0 = torch.as_tensor(np.ascontiguousarray(P0, dtype=np.float64)).to(d).contiguous()
@@ -144,11 +145,14 @@ class SourceField:
                                           dtype=torch.int32, device=d)
         self._tile_scratch = None
 
-    def interpolate(self, target: DeviceMesh, tol=1e-12):
+    def interpolate(self, target: DeviceMesh, tol=1e-12, probes_of=None):
         """``Function.interpolate`` of every snapshot onto ``target`` (Env2DAirfoil.py:556-568).
 
         Returns U [T, V+E, 2], P [T, V], cell_of [V+E] (source cell of each target dof point) and the
         device counter of points that fell outside every source cell (closest-cell extrapolation).
+        ``probes_of``: the FlowSolver whose mesh ``target`` is -- the drag / lift surface integral over its airfoil facets
+        is then evaluated by the last block of the same launch (``mdq_interpolate_drag_lift``) and left where
+        ``probes.drag_lift_device`` finds it, so the reward costs no further launch.
         """
         m0, d = self.mesh, self.mesh.device
         npt = target.nv + target.ne
@@ -172,6 +176,24 @@ class SourceField:
             if rc != 0:
                 self._tile_counters.zero_()
             _lib.check(rc, "mdq_interpolate_tiled")
+            self.last_miss_list = miss_list
+            return U, P, cell_of, miss
+        fs = probes_of
+        if fs is not None and fs.mesh is target and self.T <= 8:
+            dl = torch.empty((2, self.T), dtype=torch.float64, device=d)
+            if self._ticket is None:
+                self._ticket = torch.zeros(1, dtype=torch.int32, device=d)
+            with torch.cuda.device(d):
+                rc = L.mdq_interpolate_drag_lift(p(target.coords), target.nv, p(target.edges), target.ne, p(m0.coords),
+                                                 p(m0.cells), p(m0.cell_edges), m0.nv, m0.ne, m0.nc, self.h_grid,
+                                                 p(self.bin_ptr), p(self.bin_cells), float(tol), self.T, p(self.U0),
+                                                 p(self.P0), p(U), p(P), p(cell_of), p(miss), p(miss_list),
+                                                 p(target.cells), p(target.cell_edges), p(fs.tags), p(target.edge_cell),
+                                                 float(fs.viscosity), p(dl), p(self._ticket), _lib.stream_ptr())
+            if rc != 0:
+                self._ticket.zero_()
+            _lib.check(rc, "mdq_interpolate_drag_lift")
+            fs._dl_cache = (target, U, P, dl)
             self.last_miss_list = miss_list
             return U, P, cell_of, miss
         with torch.cuda.device(d):
@@ -475,7 +497,7 @@ class Env2DAirfoil:
             old = (fs.mesh, fs.tags, fs.removable_dev, fs.num_vertices, fs._removable_host)
             try:
                 fs.remesh(mesh)                                          # smooth(50), tags, removable on device
-                U, P, cell_of, miss = self.source.interpolate(fs.mesh)   # all T snapshots from the ORIGINAL mesh (B6)
+                U, P, cell_of, miss = self.source.interpolate(fs.mesh, probes_of=fs)   # all T snapshots from the ORIGINAL mesh (B6); drag / lift in the same launch
                 if self.interp_strict_tol is not None and \
                         self.source.miss_distance(fs.mesh, cell_of, miss) > self.interp_strict_tol:
                     raise RuntimeError("target dof point outside the source mesh by more than interp_strict_tol")

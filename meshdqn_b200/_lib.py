@@ -133,6 +133,8 @@ _SIGS = {
     "mdq_grid_fill": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
     "mdq_interpolate": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, POINTER(c_double), _P, _P,
                                 c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mdq_interpolate_drag_lift": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, POINTER(c_double), _P, _P,
+                                c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_double, _P, _P, _P]),
     "mdq_interp_miss_distance": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "mdq_interp_tiled_counter_words": (c_int64, [POINTER(mdq_tile_index_t)]),
     "mdq_interp_tiled_scratch_words": (c_int64, [POINTER(mdq_tile_index_t), c_int]),

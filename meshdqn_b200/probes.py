@@ -20,6 +20,9 @@ from . import _lib
 def drag_lift_device(fs, U, P):
     """[2, T] f64 device tensor: row 0 drag, row 1 lift, for snapshots U [T, V+E, 2], P [T, V]."""
     m = fs.mesh
+    cached = fs.__dict__.get("_dl_cache")
+    if cached is not None and cached[0] is m and cached[1] is U and cached[2] is P:
+        return cached[3]            # evaluated by the interpolation launch's epilogue (mdq_interpolate_drag_lift)
     T = int(U.shape[0])
     if U.shape[1] != m.nv + m.ne or P.shape[1] != m.nv:
         raise ValueError(f"field sizes {tuple(U.shape)}, {tuple(P.shape)} do not match mesh (V={m.nv}, E={m.ne})")

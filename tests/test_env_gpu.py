@@ -325,3 +325,25 @@ def test_fast_div_sqrt_match_operators(cuda_device):
             assert decl_div == 0 and decl_sqrt == 0, (decl_div, decl_sqrt)
         else:
             assert decl_div < n and decl_sqrt < n
+
+
+def test_fused_interpolation_drag_lift_equals_separate_launches(cuda_device):
+    """mdq_interpolate_drag_lift (the miss pass's last block integrates the airfoil facets) against mdq_interpolate followed by
+    mdq_drag_lift: identical fields, bit-identical drag / lift (one reduction shape), and the environment's reward uses it."""
+    from meshdqn_b200.probes import drag_lift_device
+    env, renv = make_envs("ys930", cuda_device)
+    env.get_state()
+    for a in (5, 40):
+        env.step(a)
+    fs = env.flow_solver
+    U1, P1, c1, m1 = env.source.interpolate(fs.mesh)                     # separate launches
+    fs.__dict__.pop("_dl_cache", None)
+    dl_sep = drag_lift_device(fs, U1, P1).clone()
+    U2, P2, c2, m2 = env.source.interpolate(fs.mesh, probes_of=fs)       # fused
+    cached = fs._dl_cache
+    assert cached[1] is U2 and cached[2] is P2
+    dl_fused = drag_lift_device(fs, U2, P2)
+    assert dl_fused is cached[3]
+    assert torch.equal(U1, U2) and torch.equal(P1, P2) and torch.equal(c1, c2)
+    assert torch.equal(dl_sep, dl_fused)
+    assert torch.isfinite(dl_fused).all() and dl_fused.abs().max() > 0
