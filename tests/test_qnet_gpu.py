@@ -230,3 +230,22 @@ def test_torch_ops_layer(cuda_device):
     d = torch.ops.meshdqn_b200.polygon_distance(coords, idx, ring)
     inside = ((coords[idx.long()] > 0.2) & (coords[idx.long()] < 0.8)).all(1)
     assert torch.equal(d == 0, inside)
+
+
+def test_candidate_variants_q_eval_matches_oracle(cuda_device):
+    """BASELINE.json configs[4]: one-vertex-removed variants (candidates.py: local star re-triangulation, window re-cut)
+    scored as ONE batch -- Q and the chosen action against the oracle, graph by graph."""
+    import numpy as np
+    from meshdqn_b200 import candidates as C
+    from meshdqn_b200.synthetic import field_values, synthetic_airfoil_mesh
+    coords, cells, n_ring = synthetic_airfoil_mesh(6000, seed=3)
+    u, p = field_values(coords, 5, 0)
+    graphs, meta = C.candidate_state_graphs(coords, cells, np.arange(4, 4 + n_ring), u, p, n_candidates=64, n_closest=180)
+    assert len(graphs) >= 60
+    net, ref = make_nets(cuda_device, lively=True)
+    with torch.no_grad():
+        am, q = net.select_action(Batch.from_data_list(graphs).to(cuda_device))
+        q_ref = ref(Batch.from_data_list(graphs))
+    assert torch.equal(am.cpu().long(), q_ref.argmax(1))
+    assert (q.cpu() - q_ref).abs().max() <= 2e-5
+    assert len({int(a) for a in am.cpu()}) > 1 or q_ref.std() > 0
