@@ -644,6 +644,9 @@ def measure_extras(dev, net, rb_dev, flush, args):
         env = mk()
         s = env.get_state()
         rng = np.random.RandomState(0)
+        for _ in range(3):              # warm-up: first-use allocations, the torch.ops layer's one-off set-up
+            am, _ = net.select_action(s)
+            s, r, done, _ = env.step(int(rng.randint(0, 180)))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         n = 0

@@ -293,6 +293,7 @@ class ReplayTrainer:
         self.early_tail = os.environ.get("MDQ_EARLY_TAIL") == "1" and not any(
             k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR"))
         self._sync = None
+        self.merged_graph = os.environ.get("MDQ_SPLIT_GRAPHS") != "1"
         # graphs=True: the launches of a step (everything but the NCCL all-reduce) are captured once per (select branch,
         # minibatch buffers) and replayed -- the ~13 launches cost ~200 us of host time per step otherwise, more than
         # the kernels.  Needs minibatches at fixed device addresses (the same ReplayBatch, or DevicePrefetcher(static=True)).
@@ -463,7 +464,16 @@ class ReplayTrainer:
         fused=False: the reference's literal sequence forward(Q1), forward(Q2), Huber, backward (used by tests)."""
         if not fused or self.timers is not None or not self.overlap:
             return self._step_serial(batch, fused)
-        r = self._roles(batch)
+        static = getattr(batch, "static", False)
+        cache = batch.__dict__.setdefault("_step_cache", {}) if static else None
+        ck = (id(self), self.select)
+        hit = cache.get(ck) if cache is not None else None
+        if hit is None:
+            r = self._roles(batch)
+            hit = (r, self._graph_key(batch, lr=False) if static else None)
+            if cache is not None:
+                cache[ck] = hit             # a static batch's tensors stay where they are: argument lists and key parts too
+        r, key_part = hit
         sel, args, mode, index, other, o_args = r
         if args is None:                    # every transition terminal and the next-state net selected: nothing to train on
             return self._step_serial(batch, fused)
@@ -471,10 +481,10 @@ class ReplayTrainer:
         net = self.nets[sel]
         main = torch.cuda.current_stream(dev)
         side, upd = self._streams(dev)
-        use_graph = self.graphs and getattr(batch, "static", False)
+        use_graph = self.graphs and static
         entry = None
         if use_graph:
-            key = self._graph_key(batch)
+            key = (multistep_lr(self.lr, self.num_grads),) + key_part
             entry = self._graphs.get(key)
             if entry is None:
                 if key in self._seen:
@@ -491,44 +501,43 @@ class ReplayTrainer:
             sync = self._early(r, dev)
             if sync is not None:
                 q_buf = torch.empty((int(o_args[4]), other._net.out_dim), dtype=torch.float32, device=dev)
-        inputs_ready = torch.cuda.Event()
-        inputs_ready.record(main)
-
-        def run_A():      # main stream; only a freshly de-selected net still has an update in flight
+        if entry is not None:
+            # graph replay: ONE launch for H || A -> T (the fork to the side stream and the join are inside the captured
+            # graph), one for U -- the host issues two launches per step instead of four, which matters because four graph
+            # launches cost about as much host time as the step's kernels take
+            if pend_net is not None:
+                main.wait_event(pend_net)
             if pend_other is not None:
                 main.wait_event(pend_other)
-            if entry is not None:
+            if self.merged_graph:
+                entry["HAT"].replay()
+            else:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    entry["H"].replay()
                 entry["A"].replay()
-                return entry["q_other"]
-            return self._seg_A(r, q_buf, sync)
-
-        def run_H():      # side stream: after the inputs and the selected net's previous update, beside A
+                main.wait_stream(side)
+                entry["T"].replay()
+            loss = entry["loss"]
+        else:
+            inputs_ready = torch.cuda.Event()
+            inputs_ready.record(main)
+            # kernel by kernel.  A is ENQUEUED first (main stream; only a freshly de-selected net still has an update in
+            # flight): an early-launched tail (in H) waits on the device for A's post, and with A already in the queue
+            # nothing the host does afterwards -- a first-use cudaMalloc that synchronises the device, an exception -- can
+            # keep that post from arriving.
+            if pend_other is not None:
+                main.wait_event(pend_other)
+            q_other = self._seg_A(r, q_buf, sync)
+            # H on the side stream: after the inputs and the selected net's previous update, beside A
             side.wait_event(inputs_ready)
             if pend_net is not None:
                 side.wait_event(pend_net)
             with torch.cuda.stream(side):
-                if entry is not None:
-                    entry["H"].replay()
-                else:
-                    self._seg_H(batch, r, scalar, loss, q_buf, sync)
-                    if q_buf is not None:
-                        q_buf.record_stream(side)
-
-        # Queue order.  An early-launched tail (in H) waits on the device for A's post.  Replaying graphs, the host does
-        # nothing between the two replays, and H goes first so that its tail starts as early as possible (it is the long
-        # pole: stage 0 -> stage 1 -> tail).  Launching kernel by kernel, A goes first: whatever the host does afterwards --
-        # a first-use cudaMalloc that synchronises the device, an exception -- the post is already in the queue.
-        if entry is not None:
-            run_H()
-            q_other = run_A()
-        else:
-            q_other = run_A()
-            run_H()
-        main.wait_stream(side)
-        if entry is not None:
-            entry["T"].replay()
-            loss = entry["loss"]
-        else:
+                self._seg_H(batch, r, scalar, loss, q_buf, sync)
+                if q_buf is not None:
+                    q_buf.record_stream(side)
+            main.wait_stream(side)
             self._seg_T(batch, r, q_other, scalar, loss, 2 if sync is None else 4)
         # U on the update stream
         ev = torch.cuda.Event()
@@ -547,12 +556,13 @@ class ReplayTrainer:
         self._after_step(net, sel, fresh=True)
         return loss
 
-    def _graph_key(self, batch):
+    def _graph_key(self, batch, lr=True):
         t = [batch.states.x, batch.states.edge_index, batch.actions, batch.rewards, batch.next_slot, batch.owner]
         t += list(graph_ptrs(batch.states)[:2])
         if batch.next_states is not None:
             t += [batch.next_states.x, batch.next_states.edge_index] + list(graph_ptrs(batch.next_states)[:2])
-        return (self.select, multistep_lr(self.lr, self.num_grads)) + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
+        head = (self.select, multistep_lr(self.lr, self.num_grads)) if lr else (self.select,)
+        return head + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
 
     def _capture(self, batch, key, r):
         """Capture the four segments on these minibatch buffers (the second time the buffers show up: minibatches that
@@ -578,18 +588,32 @@ class ReplayTrainer:
         L = _lib.lib()
         n0 = int(L.mdq_launch_count())
         pool = torch.cuda.graph_pool_handle()
-        for name in ("H", "A", "T", "U"):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                if name == "H":
-                    self._seg_H(batch, r, scalar, loss, q_buf, sync)
-                elif name == "A":
-                    entry["q_other"] = self._seg_A(r, q_buf, sync)
-                elif name == "T":
-                    self._seg_T(batch, r, entry["q_other"], scalar, loss, 2 if sync is None else 4)
-                else:
-                    self._seg_U(sel)
-            entry[name] = g
+        side, _ = self._streams(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            cap = torch.cuda.current_stream(dev)        # the capture stream: fork to the side stream, join back
+            side.wait_stream(cap)
+            with torch.cuda.stream(side):
+                self._seg_H(batch, r, scalar, loss, q_buf, sync)
+            entry["q_other"] = self._seg_A(r, q_buf, sync)
+            cap.wait_stream(side)
+            self._seg_T(batch, r, entry["q_other"], scalar, loss, 2 if sync is None else 4)
+        entry["HAT"] = g
+        if not self.merged_graph:            # the three segments as separate launches (A/B of the host cost)
+            for name in ("H", "A", "T"):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    if name == "H":
+                        self._seg_H(batch, r, scalar, loss, q_buf, sync)
+                    elif name == "A":
+                        self._seg_A(r, entry["q_other"], sync)
+                    else:
+                        self._seg_T(batch, r, entry["q_other"], scalar, loss, 2 if sync is None else 4)
+                entry[name] = g
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            self._seg_U(sel)
+        entry["U"] = g
         entry["n"] = int(L.mdq_launch_count()) - n0
         L.mdq_launch_count_add(-entry["n"])             # recorded, not run
         net._staged_mark_fresh()                        # the forced refresh inside U was only recorded

@@ -13,8 +13,8 @@ nets = []
 for _ in range(2):
     n = NodeRemovalNet(181, 128, 0.1); n.set_num_nodes(17); nets.append(n.to(dev))
 trans = [(mk(), int(torch.randint(0, 181, (1,), generator=g)), None if i % 9 == 0 else mk(), float(torch.randn(1, generator=g))) for i in range(256)]
-rb = ReplayBatch.from_transitions(trans).to(dev)
-tr = ReplayTrainer(nets[0], nets[1])
+rb = ReplayBatch.from_transitions(trans).pin_memory(slim=True).to(dev).mark_static()
+tr = ReplayTrainer(nets[0], nets[1], graphs=True, target_update=1000)
 for _ in range(10):
     tr.step(rb)
 torch.cuda.synchronize()
