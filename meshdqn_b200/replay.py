@@ -562,7 +562,10 @@ class ReplayTrainer:
         if batch.next_states is not None:
             t += [batch.next_states.x, batch.next_states.edge_index] + list(graph_ptrs(batch.next_states)[:2])
         head = (self.select, multistep_lr(self.lr, self.num_grads)) if lr else (self.select,)
-        return head + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
+        sizes = tuple(graph_ptrs(batch.states)[2:])           # graph count and size bounds are launch arguments
+        if batch.next_states is not None:
+            sizes += tuple(graph_ptrs(batch.next_states)[2:])
+        return head + sizes + tuple((x.data_ptr(), tuple(x.shape)) for x in t)
 
     def _capture(self, batch, key, r):
         """Capture the four segments on these minibatch buffers (the second time the buffers show up: minibatches that
@@ -573,7 +576,7 @@ class ReplayTrainer:
         dev = batch.states.x.device
         net = self.nets[sel]
         torch.cuda.synchronize(dev)
-        if len(self._graphs) >= 16:
+        if len(self._graphs) >= 128:
             self._graphs.pop(next(iter(self._graphs)))
         other._staged_refresh()
         net._staged_refresh()
@@ -708,6 +711,7 @@ class DeviceReplayMemory:
         self.h_has_next = np.zeros(self.capacity, dtype=bool)
         self.size, self.head = 0, 0
         self._ring, self._ring_pos = [], 0
+        self.max_nodes_seen, self.max_edges_seen = 0, 0     # over everything ever stored (upper bounds for static sampling)
 
     def __len__(self):
         return self.size
@@ -736,6 +740,7 @@ class DeviceReplayMemory:
                                     max(self.e_max, 1), _lib.stream_ptr())
         _lib.check(rc, "mdq_replay_store")
         self.h_nn[side, slot], self.h_ne[side, slot] = n, E
+        self.max_nodes_seen, self.max_edges_seen = max(self.max_nodes_seen, n), max(self.max_edges_seen, E)
 
     def push(self, state, action, next_state, reward):
         """One ``Transition(state, action, next_state, reward)`` (airfoil_dqn.py:46-47,58-60); ``next_state`` None = terminal."""
@@ -854,4 +859,106 @@ class DeviceReplayMemory:
                    n_next, mx[2], mx[3]) if with_next else None
         out = ReplayBatch(states, act, nexts, v32[4], rew, v32[5])
         out._keep = meta                  # the metadata block backs the offset views
+        return out
+
+    def static_sampler(self, batch_size):
+        """A sampler whose minibatches live in FIXED device buffers (see ``StaticSampler``)."""
+        return StaticSampler(self, batch_size)
+
+
+class StaticSampler:
+    """Minibatches of a ``DeviceReplayMemory`` at fixed device addresses and fixed tensor shapes, so that
+    ``ReplayTrainer(graphs=True)`` replays its captured step on them: the step's launch arguments then depend only on the
+    number of non-terminal transitions in the draw (the next-state batch's graph count), which becomes part of the graph
+    key -- a few dozen values at B = 256, each captured on its second sighting.
+
+    Buffers are sized for the worst case (B graphs of ``n_max`` nodes / ``e_max`` edges; edge rows ``B * e_max`` apart);
+    the kernels read sizes from the offset vectors, never from tensor shapes.  ``sample`` overwrites the previous
+    minibatch in stream order: enqueue it on the stream the trainer steps on, after the step that used the last one.
+    Per draw the host does what ``DeviceReplayMemory.sample`` does (index draw, cumulative sums, one pinned block, one
+    H2D copy of ~12 KB, one gather launch) but allocates nothing."""
+
+    def __init__(self, mem: "DeviceReplayMemory", batch_size):
+        self.mem, self.B = mem, int(batch_size)
+        B, d = self.B, mem.device
+        N, E = B * mem.n_max, B * max(mem.e_max, 1)
+        f32, i64, i32 = dict(dtype=torch.float32, device=d), dict(dtype=torch.int64, device=d), dict(dtype=torch.int32, device=d)
+        self.x = [torch.zeros((N, mem.F), **f32) for _ in range(2)]
+        self.ei = [torch.zeros((2, E), **i64) for _ in range(2)]
+        self.bvec = [torch.zeros(N, **i64) for _ in range(2)]
+        self.act, self.rew = torch.zeros(B, **i32), torch.zeros(B, **f32)
+        self.n64 = B + 4 * (B + 1)
+        self.n32 = 4 * (B + 1) + 2 * B
+        self.meta = torch.zeros(8 * self.n64 + 4 * self.n32, dtype=torch.uint8, device=d)
+        self.E = E
+
+    def sample(self, rng=None, idx=None) -> "ReplayBatch":
+        from .data import Batch
+        mem, B = self.mem, self.B
+        np = mem._np
+        if idx is None:
+            if B > mem.size:
+                raise ValueError(f"sample of {B} from a memory of {mem.size}")
+            idx = (rng if rng is not None else np.random).choice(mem.size, B, replace=False)
+        idx = np.asarray(idx, dtype=np.int64)
+        if len(idx) != B:
+            raise ValueError(f"this sampler draws minibatches of {B}")
+        has_next = mem.h_has_next[idx]
+        n_next = int(has_next.sum())
+        n64, n32 = self.n64, self.n32
+        nbytes = 8 * n64 + 4 * n32
+        slot = mem._meta_block(nbytes)
+        hb = slot[0].numpy()
+        w64 = hb[:8 * n64].view(np.int64)
+        w32 = hb[8 * n64:nbytes].view(np.int32)
+        G = B + 1                                     # fixed section sizes: every offset vector has room for B graphs
+        w64[:B] = idx
+        ptr, eptr, nptr, neptr = (w64[B + i * G:B + (i + 1) * G] for i in range(4))
+        ptr[0] = eptr[0] = 0
+        nptr[:] = 0
+        neptr[:] = 0
+        np.cumsum(mem.h_nn[0, idx], out=ptr[1:])
+        np.cumsum(mem.h_ne[0, idx], out=eptr[1:])
+        if n_next:
+            nidx = idx[has_next]
+            np.cumsum(mem.h_nn[1, nidx], out=nptr[1:n_next + 1])
+            np.cumsum(mem.h_ne[1, nidx], out=neptr[1:n_next + 1])
+            nptr[n_next + 1:] = nptr[n_next]
+            neptr[n_next + 1:] = neptr[n_next]
+        for i, v in enumerate((ptr, eptr, nptr, neptr)):
+            w32[i * G:(i + 1) * G] = v
+        w32[4 * G:4 * G + B] = np.where(has_next, np.cumsum(has_next) - 1, -1)      # next_slot
+        w32[4 * G + B:4 * G + 2 * B] = 0
+        if n_next:
+            w32[4 * G + B:4 * G + B + n_next] = np.nonzero(has_next)[0]              # owner
+        self.meta.copy_(slot[0][:nbytes], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+        m64 = self.meta[:8 * n64].view(torch.int64)
+        m32 = self.meta[8 * n64:].view(torch.int32)
+        v64 = [m64[:B]] + [m64[B + i * G:B + (i + 1) * G] for i in range(4)]
+        v32 = [m32[i * G:(i + 1) * G] for i in range(4)] + [m32[4 * G:4 * G + B], m32[4 * G + B:4 * G + 2 * B]]
+        with_next = n_next > 0
+        L, q = _lib.lib(), _lib.ptr
+        with torch.cuda.device(mem.device):
+            rc = L.mdq_replay_gather(q(mem.x[0]), q(mem.ei[0]), q(mem.nn[0]), q(mem.ne[0]), q(mem.x[1]), q(mem.ei[1]),
+                                     q(mem.nn[1]), q(mem.ne[1]), mem.n_max, max(mem.e_max, 1), mem.F, q(v64[0]), B,
+                                     q(v32[0]), q(v32[1]), self.E, q(self.x[0]), q(self.ei[0]), q(self.bvec[0]), q(v32[4]),
+                                     q(v32[2]), q(v32[3]), self.E, q(self.x[1]) if with_next else None,
+                                     q(self.ei[1]) if with_next else None, q(self.bvec[1]) if with_next else None,
+                                     q(mem.actions), q(mem.rewards), q(self.act), q(self.rew), _lib.stream_ptr())
+        _lib.check(rc, "mdq_replay_gather")
+        mn, me = max(mem.max_nodes_seen, 1), max(mem.max_edges_seen, 1)
+
+        def mk(side, p64, e64, p32, e32, Gn):
+            b = Batch(x=self.x[side], edge_index=self.ei[side])
+            b.batch, b.ptr, b.eptr, b.num_graphs = self.bvec[side], p64, e64, Gn
+            b.__dict__["_mdq_ptrs"] = (p32, e32, Gn, mn, me)
+            b.__dict__["_meta"] = b.__dict__["_mdq_ptrs"]
+            return b
+        states = mk(0, v64[1], v64[2], v32[0], v32[1], B)
+        nexts = mk(1, v64[3][:n_next + 1], v64[4][:n_next + 1], v32[2][:n_next + 1], v32[3][:n_next + 1], n_next) if with_next else None
+        out = ReplayBatch(states, self.act, nexts, v32[4], self.rew, v32[5][:max(n_next, 1)])
+        out.static = True
         return out

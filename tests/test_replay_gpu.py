@@ -189,3 +189,56 @@ def test_device_replay_memory_matches_host_collation(cuda_device):
     assert drawn.states.num_graphs == 16 and int(drawn.states.ptr[-1]) == drawn.states.x.shape[0]
     with pytest.raises(ValueError):
         mem.push(Data(x=torch.randn(181, 17), edge_index=torch.zeros((2, 0), dtype=torch.long)).to(cuda_device), 0, None, 0.0)
+
+
+def test_static_sampler_replays_graphs_across_draws(cuda_device):
+    """DeviceReplayMemory.static_sampler: minibatches at fixed addresses / shapes.  (1) the same transitions give the same
+    collated content as ``sample`` (up to the padding the kernels never read); (2) a graph-replaying trainer fed by the static
+    sampler and a plain trainer fed by ``sample`` with the same draws stay bit-identical over 40 steps in which the number of
+    non-terminal transitions (a launch argument, hence part of the graph key) varies."""
+    from meshdqn_b200.airfoilgcnn import NodeRemovalNet
+    from meshdqn_b200.replay import DeviceReplayMemory, ReplayTrainer
+    g = torch.Generator().manual_seed(12)
+
+    def mk():
+        n = int(torch.randint(150, 181, (1,), generator=g))
+        e = int(torch.randint(300, 400, (1,), generator=g))
+        return Data(x=torch.randn(n, 17, generator=g), edge_index=torch.randint(0, n, (2, e), generator=g))
+    mem = DeviceReplayMemory(capacity=64, n_max=180, e_max=400, n_features=17, device=cuda_device)
+    for i in range(64):
+        s2 = None if i % 5 == 2 else mk()
+        mem.push(mk().to(cuda_device), int(torch.randint(0, 181, (1,), generator=g)), None if s2 is None else s2.to(cuda_device),
+                 float(torch.rand(1, generator=g)))
+    B = 16
+    smp = mem.static_sampler(B)
+    idx = [3, 7, 12, 40, 41, 2, 63, 22, 17, 5, 9, 31, 50, 27, 0, 33]
+    a, b = smp.sample(idx=idx), mem.sample(B, idx=idx)
+    N, E = int(b.states.x.shape[0]), int(b.states.edge_index.shape[1])
+    assert torch.equal(a.states.x[:N], b.states.x) and torch.equal(a.states.edge_index[:, :E], b.states.edge_index)
+    Nn, En = int(b.next_states.x.shape[0]), int(b.next_states.edge_index.shape[1])
+    assert torch.equal(a.next_states.x[:Nn], b.next_states.x) and torch.equal(a.next_states.edge_index[:, :En], b.next_states.edge_index)
+    assert torch.equal(a.actions, b.actions) and torch.equal(a.rewards, b.rewards) and torch.equal(a.next_slot, b.next_slot)
+    assert torch.equal(a.owner, b.owner) and a.next_states.num_graphs == b.next_states.num_graphs
+    assert torch.equal(a.states._mdq_ptrs[0], b.states._mdq_ptrs[0]) and torch.equal(a.next_states._mdq_ptrs[1], b.next_states._mdq_ptrs[1])
+    out = {}
+    for name in ("static_graphs", "plain"):
+        torch.manual_seed(1370)
+        nets = []
+        for _ in range(2):
+            n = NodeRemovalNet(181, 128, 0.1)
+            n.set_num_nodes(17)
+            nets.append(n.to(cuda_device))
+        tr = ReplayTrainer(nets[0], nets[1], lr=1e-4, weight_decay=1e-6, gamma=1.0, target_update=7, graphs=name == "static_graphs")
+        rng = np.random.RandomState(5)
+        losses, nnext = [], set()
+        for k in range(40):
+            batch = smp.sample(rng=rng) if name == "static_graphs" else mem.sample(B, rng=rng)
+            nnext.add(batch.next_states.num_graphs)
+            losses.append(float(tr.step(batch)))
+        tr.flush()
+        torch.cuda.synchronize()
+        out[name] = (losses, nets[0]._flat.clone(), nets[1]._flat.clone(), len(tr._graphs), nnext)
+    assert len(out["plain"][4]) >= 3                    # the draws really differ in their number of next states
+    assert out["static_graphs"][3] >= 2                 # ... and several (select, n_next) keys were captured and replayed
+    assert out["static_graphs"][0] == out["plain"][0]
+    assert torch.equal(out["static_graphs"][1], out["plain"][1]) and torch.equal(out["static_graphs"][2], out["plain"][2])
