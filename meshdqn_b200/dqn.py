@@ -86,7 +86,7 @@ def load_policy_nets(save_prefix, net1, net2, map_location="cpu"):
 
 def train(make_env, net1, net2, *, episodes, batch_size=32, lr=1e-5, weight_decay=1e-6, gamma=1.0, target_update=50,
           eps_start=1.0, eps_end=0.01, eps_decay=10000.0, memory_capacity=10000, device=None, save_prefix=None,
-          seed=137, max_steps_per_episode=None, handler=None, memory=None, verbose=False):
+          seed=137, max_steps_per_episode=None, handler=None, memory=None, verbose=False, graphs=False):
     """Single-process epsilon-greedy DQN (the loop of airfoil_dqn.py:428-503).  ``make_env()`` builds an
     ``Env2DAirfoil``; ``net1`` / ``net2`` are the two policy nets (on ``device``).  Returns the ``DataHandler``."""
     from .replay import DeviceReplayMemory, ReplayTrainer
@@ -94,7 +94,8 @@ def train(make_env, net1, net2, *, episodes, batch_size=32, lr=1e-5, weight_deca
     rng = np.random.RandomState(seed)                       # np.random.seed(137) at :424, one stream here
     random.seed(seed)
     handler = handler or DataHandler(save_prefix or "./")
-    trainer = ReplayTrainer(net1, net2, lr=lr, weight_decay=weight_decay, gamma=gamma, target_update=target_update)
+    trainer = ReplayTrainer(net1, net2, lr=lr, weight_decay=weight_decay, gamma=gamma, target_update=target_update, graphs=graphs)
+    sampler = None                                          # graphs=True: minibatches in fixed buffers (StaticSampler)
     env = make_env()
     n_actions = int(env.N_CLOSEST)
     steps_done = handler.num_eps() / 14 if handler.num_eps() else 0       # :436 (restart quirk kept)
@@ -128,7 +129,10 @@ def train(make_env, net1, net2, *, episodes, batch_size=32, lr=1e-5, weight_deca
             state = next_state
             loss = None
             if len(memory) >= batch_size:                   # optimize_model (:314-335)
-                loss = float(trainer.step(memory.sample(batch_size, rng=rng)))
+                if graphs and sampler is None:
+                    sampler = memory.static_sampler(batch_size)
+                mb = sampler.sample(rng=rng) if sampler is not None else memory.sample(batch_size, rng=rng)
+                loss = float(trainer.step(mb))
                 handler.add_loss(loss)
             handler.add_eps(eps)
             t += 1
@@ -256,6 +260,7 @@ def train_replicas(make_env, net1, net2, *, n_envs, rounds, batch_size=32, lr=1e
         s0 = workers.states[0]
         e_max = max(6 * int(s0.x.shape[0]), 2 * int(s0.edge_index.shape[1]))
         memory = DeviceReplayMemory(memory_capacity, int(s0.x.shape[0]), e_max, int(s0.x.shape[1]), dev)
+        sampler = None                                      # graphs=True: minibatches in fixed buffers (StaticSampler)
         ep_actions = [[] for _ in range(n_envs)]
         ep_rewards = [[] for _ in range(n_envs)]
         steps_done = 0
@@ -282,7 +287,10 @@ def train_replicas(make_env, net1, net2, *, n_envs, rounds, batch_size=32, lr=1e
                     workers.reset(i)
             for i in range(n_envs):
                 if len(memory) >= batch_size:
-                    loss = float(trainer.step(memory.sample(batch_size, rng=rng)))
+                    if graphs and sampler is None:
+                        sampler = memory.static_sampler(batch_size)
+                    mb = sampler.sample(rng=rng) if sampler is not None else memory.sample(batch_size, rng=rng)
+                    loss = float(trainer.step(mb))
                     handler.add_loss(loss)
                 handler.add_eps(epss[i])
             if verbose and rank == 0:

@@ -64,17 +64,17 @@ def test_replica_actor_loop_is_reproducible_and_trains(cuda_device, tmp_path):
     leak into the result: two runs from the same seeds give identical actions, losses and weights."""
     from meshdqn_b200 import dqn
     runs = []
-    for rep in range(2):
+    for rep in range(3):
         mk, nets = _mk_env_and_nets(cuda_device)
         pre = str(tmp_path / f"run{rep}" / "ah93w145_")
         with contextlib.redirect_stdout(io.StringIO()):
             h = dqn.train_replicas(mk, nets[0], nets[1], n_envs=3, rounds=6, batch_size=4, eps_decay=8.0, target_update=3,
-                                   memory_capacity=64, device=cuda_device, save_prefix=pre)
+                                   memory_capacity=64, device=cuda_device, save_prefix=pre, graphs=rep == 2)   # run 2: static sampler + graph replay
         runs.append((h, {k: v.clone() for k, v in nets[0].state_dict().items()}))
         assert len(h.epss) == 18 and h.epss[0] == 1.0 and h.epss[-1] < 0.2
         assert len(h.losses) == 18 - 3 and all(np.isfinite(h.losses))            # memory reaches 4 in round 2 (3 + 3 pushes)
         assert sum(len(a) for a in h.actions) == 18
         assert torch.load(pre + "policy_net_1.pt")["lin3.weight"].shape[0] == 181
-    (h0, w0), (h1, w1) = runs
-    assert h0.actions == h1.actions and h0.losses == h1.losses
-    assert all(torch.equal(w0[k], w1[k]) for k in w0)
+    (h0, w0), (h1, w1), (h2, w2) = runs
+    assert h0.actions == h1.actions == h2.actions and h0.losses == h1.losses == h2.losses
+    assert all(torch.equal(w0[k], w1[k]) and torch.equal(w0[k], w2[k]) for k in w0)
