@@ -27,7 +27,7 @@ void stg_geom(const mdq_net_t &net, int B, int max_n, int max_e, StgGeom &G)
     G.R2 = topk_count(net.ratio, G.R1);
     G.EC = (max_e > 0 ? max_e : 1);
     G.EC = (G.EC + 7) & ~7;
-    int gs1 = stg_env_int("MDQ_STG_GS1", 2), gs2 = stg_env_int("MDQ_STG_GS2", 8);
+    int gs1 = stg_env_int("MDQ_STG_GS1", 2), gs2 = stg_env_int("MDQ_STG_GS2", 4);
     while (gs1 > 1 && gs1 * G.R1 > 128) --gs1;
     while (gs2 > 1 && gs2 * G.R2 > 32) --gs2;
     G.GS1 = gs1 < 1 ? 1 : gs1;
