@@ -281,7 +281,8 @@ int stg_backward_launch(const StgCall &c, int B, int max_n, int max_e, stg::TArg
         a.rp_reward = a2.rp_reward; a.rp_action = a2.rp_action; a.next_slot = ls.next_slot; a.loss = ls.loss;
         const int bytes = stg::b1_layout(a);
         if ((rc = stg_smem_attr(stg::k_bwd1, bytes, "k_bwd1")) != MDQ_OK) return rc;
-        stg::k_bwd1<<<(B + G.GS1 - 1) / G.GS1, stg::NTH_TAIL, bytes, st>>>(a);
+        // + 1: the loss-reduction CTA (modes 1 / 2)
+        stg::k_bwd1<<<(B + G.GS1 - 1) / G.GS1 + (a.mode != 0 ? 1 : 0), stg::NTH_TAIL, bytes, st>>>(a);
         if ((rc = mdq::check_launch("k_bwd1")) != MDQ_OK) return rc;
     }
     wgrad_partial_kernel<<<n_tasks > 0 ? n_tasks : 1, 256, 0, st>>>(wd, B, workspace, d_partial);

@@ -729,6 +729,28 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_bwd1(const __grid_constant__ B1
     extern __shared__ __align__(128) unsigned char sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int GS = a.GS, R1 = a.R1, R2 = a.R2;
+    if (blockIdx.x * GS >= a.B) {
+        // one extra CTA (launched when the loss is wanted): the batch loss from the per-transition Huber terms, beside the
+        // working CTAs instead of at the end of CTA 0 (which made CTA 0 the last one to finish)
+        if (tid >= NTH || a.mode == 0) return;
+        float *red = reinterpret_cast<float *>(sm);
+        float sum = 0.f;
+        for (int g = tid; g < a.B; g += NTH) sum += a.lterm[g];
+        if (a.mode == 2)
+            for (int b = tid; b < a.batch; b += NTH)
+                if (a.next_slot[b] < 0) {
+                    const float d = a.rp_qother[(size_t)b * a.A + a.rp_action[b]] - a.rp_reward[b];
+                    sum += (fabsf(d) < 1.f) ? 0.5f * d * d : (fabsf(d) - 0.5f);
+                }
+        red[tid] = sum;
+        cta_sync();
+        for (int o = NTH / 2; o; o >>= 1) {
+            if (tid < o) red[tid] += red[tid + o];
+            cta_sync();
+        }
+        if (tid == 0) *a.loss = red[0] / (float)a.batch;
+        return;
+    }
     const int g0 = blockIdx.x * GS, ng = min(GS, a.B - g0);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm);
     float *dP2 = reinterpret_cast<float *>(sm + a.o_dp2), *dcat = reinterpret_cast<float *>(sm + a.o_dcat);
@@ -938,25 +960,6 @@ __global__ void __launch_bounds__(NTH_TAIL, 1) k_bwd1(const __grid_constant__ B1
             acc += tds0[lr] * (H1[(size_t)lr * LDW + c] / wn1 - z1[lr] * wc / wn2);
         }
         a.pool1_d[(size_t)(g0 + gi) * 128 + c] = acc;
-    }
-    if (a.mode != 0 && blockIdx.x == 0) {
-        cta_sync();
-        float *red = dX1;   // scratch: dX1 is dead
-        float sum = 0.f;
-        for (int g = tid; g < a.B; g += NTH) sum += a.lterm[g];
-        if (a.mode == 2)
-            for (int b = tid; b < a.batch; b += NTH)
-                if (a.next_slot[b] < 0) {
-                    const float d = a.rp_qother[(size_t)b * a.A + a.rp_action[b]] - a.rp_reward[b];
-                    sum += (fabsf(d) < 1.f) ? 0.5f * d * d : (fabsf(d) - 0.5f);
-                }
-        red[tid] = sum;
-        cta_sync();
-        for (int o = NTH / 2; o; o >>= 1) {
-            if (tid < o) red[tid] += red[tid + o];
-            cta_sync();
-        }
-        if (tid == 0) *a.loss = red[0] / (float)a.batch;
     }
     STG_TRACE(a.trace, 256, 5);  // end
     STG_GT(a.trace, 15);
