@@ -214,8 +214,9 @@ int mdq_adam_step(float *params, const float *grad, float *exp_avg, float *exp_a
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
                   void *stream);
 
-/* Same update with the step count kept on the device (step_dev[0] = steps taken so far, incremented by the call): no
- * host-computed bias corrections in the launch arguments, so a captured CUDA graph of the training step stays valid. */
+/* Same update with the step count kept on the device: step_dev is TWO int32, [0] = steps taken so far (advanced by the
+ * kernel's last block), [1] = block ticket, both zero before the first call.  No host-computed bias corrections in the
+ * launch arguments, so a captured CUDA graph of the training step stays valid. */
 int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, float grad_scale, int32_t *step_dev,
                       void *stream);

@@ -1773,14 +1773,29 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 }
 
 // Adam with the step count on the device (CUDA-graph friendly: no host-computed bias corrections in the arguments).
-// step_dev[0] = steps taken so far; this launch is step t = step_dev[0] + 1; k_step_inc bumps the counter afterwards.
+// step_dev[0] = steps taken so far; this launch is step t = step_dev[0] + 1 and advances the counter when its last block ends.
+// The last block to finish advances the device step counter (step_dev[0]; step_dev[1] is the block ticket): every block
+// has read the counter by then, and no separate launch sits between the optimizer and what waits for it.
+__device__ __forceinline__ void step_done(int *step_dev, int t0)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(reinterpret_cast<unsigned *>(step_dev + 1), 1u) == gridDim.x - 1) {
+            step_dev[1] = 0;
+            step_dev[0] = t0 + 1;
+        }
+    }
+}
+
 __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                 float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
-                                float gscale, const int *__restrict__ step_dev)
+                                float gscale, int *__restrict__ step_dev)
 {
     __shared__ float sh[2];
+    const int t0 = step_dev[0];
     if (threadIdx.x == 0) {
-        const double t = (double)(step_dev[0] + 1);
+        const double t = (double)(t0 + 1);
         const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
         sh[0] = (float)((double)lr / bc1);
         sh[1] = (float)sqrt(bc2);
@@ -1799,8 +1814,8 @@ __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
         p[i] = pi - step_size * (mi / denom);
     }
+    step_done(step_dev, t0);
 }
-__global__ void k_step_inc(int *step_dev) { step_dev[0] += 1; }
 
 // ------------------------------------------------------------------------------------------------
 // Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel replay training).
@@ -1878,7 +1893,7 @@ __device__ __forceinline__ void ar_signal_and_wait(const ArArgs &ar, unsigned *c
 __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, float *__restrict__ p, const float *__restrict__ g,
                                                            float *__restrict__ m, float *__restrict__ v, int64_t n, float lr,
                                                            float b1, float b2, float eps, float wd,
-                                                           const int *__restrict__ step_dev, unsigned *block_counter)
+                                                           int *__restrict__ step_dev, unsigned *block_counter)
 {
     __shared__ float sh[2];
     const int t = step_dev[0];
@@ -1950,6 +1965,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(const ArArgs ar, fl
     }
     AR_STAMP(5)
 #undef AR_STAMP
+    step_done(step_dev, t);
 }
 
 int setup_launch(const mdq_net_t *net, int max_n, int max_e, int G, int bwd, QLay &L, WChunks *ck, void (*kern)(const QArgs))
@@ -2221,10 +2237,7 @@ int mdq_allreduce_adam(float *params, const float *grad, float *exp_avg, float *
     if (blocks > 132) blocks = 132;          // every block must be resident while it waits for the peers' flags
     allreduce_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ar, params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                     eps, weight_decay, step_dev, block_counter);
-    int rc = mdq::check_launch("allreduce_adam_kernel");
-    if (rc != MDQ_OK) return rc;
-    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
-    return mdq::check_launch("k_step_inc");
+    return mdq::check_launch("allreduce_adam_kernel");
 }
 
 int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
@@ -2240,10 +2253,7 @@ int mdq_adam_step_dev(float *params, const float *grad, float *exp_avg, float *e
     if (blocks > 148 * 8) blocks = 148 * 8;
     adam_dev_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                   weight_decay, grad_scale, step_dev);
-    int rc = mdq::check_launch("adam_dev_kernel");
-    if (rc != MDQ_OK) return rc;
-    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
-    return mdq::check_launch("k_step_inc");
+    return mdq::check_launch("adam_dev_kernel");
 }
 
 }  // extern "C"

@@ -313,7 +313,7 @@ class ReplayTrainer:
             net._ensure_packed()
             z = torch.zeros_like(net._flat)
             self._state[i] = dict(m=z, v=z.clone(), g=torch.zeros_like(net._flat), step=0,
-                                  step_dev=torch.zeros(1, dtype=torch.int32, device=net._flat.device))
+                                  step_dev=torch.zeros(2, dtype=torch.int32, device=net._flat.device))
         return self._state[i]
 
     def _setup_symmetric(self):

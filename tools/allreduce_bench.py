@@ -15,7 +15,7 @@ torch.cuda.set_device(dev)
 L, p = _lib.lib(), _lib.ptr
 n = int(os.environ.get("AR_N", "502000"))
 g = torch.randn(n, device=dev); par = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
-step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
 stage = symm.empty(int(L.mdq_allreduce_stage_floats(n, world)), dtype=torch.float32, device=dev); stage.zero_()
 hdl = symm.rendezvous(stage, dist.group.WORLD)
 ptrs = (ctypes.c_uint64 * world)(*[int(x) for x in hdl.buffer_ptrs])
