@@ -1820,15 +1820,11 @@ __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__
 // ------------------------------------------------------------------------------------------------
 // Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel replay training).
 // Every rank owns a "stage" buffer that all peers have mapped (torch symmetric memory does the mapping; the
-// arithmetic and the synchronisation are here): [2][n] floats (two step parities) followed by `world` flag words.
-//   1. copy the local gradient into stage[parity] (own HBM), fence; the last block to finish raises this rank's flag
-//      (= step number, so flags never need resetting) in EVERY peer's flag row;
-//   2. every block waits until all `world` flags of its own row have reached this step;
-//   3. thread i sums the peers' stage[parity][i] over NVLink in rank order -- the same order on every rank, so all ranks
-//      hold bit-identical weights -- scales by 1/world and applies the Adam update in place.
-// One launch replaces ncclAllReduce (latency-bound at 0.5 MB: ~20-40 us at 2-8 ranks) + the Adam launch.  A stage
-// parity is rewritten two steps later, which a rank can only reach after every peer has finished reading it (it must
-// have seen their flags of the step in between).  All blocks are co-resident (grid <= 148 blocks of 256 threads).
+// arithmetic and the synchronisation are here); its layout and the two-shot exchange are described at the kernel.
+// Flags carry the step number, so they never need resetting.  One launch replaces ncclAllReduce (latency-bound at
+// 0.5 MB) + the Adam launch.  A buffer parity is rewritten two steps later, which a rank can only reach after every
+// peer has finished with it (it must have seen their flags of the step in between).  All blocks are co-resident
+// (grid <= 132 blocks of 256 threads): they wait for each other's phases through a block counter.
 // ------------------------------------------------------------------------------------------------
 constexpr int AR_MAX_WORLD = 16;
 struct ArArgs {
@@ -1841,10 +1837,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Two-shot, push-only exchange (all remote traffic is posted stores, every wait polls LOCAL memory):
