@@ -74,3 +74,35 @@ def test_candidate_state_graphs_invariants():
     assert len(seen) > 1                                                 # the variants differ
     g2, m2 = C.candidate_state_graphs(coords, cells, ring_ids, u, p, n_candidates=400, n_closest=180)
     assert np.array_equal(meta, m2) and all(torch.equal(a.edge_index, b.edge_index) for a, b in zip(graphs[:50], g2[:50]))
+
+
+def test_throughput_mode_delta_equals_full_recompute():
+    """oracle/candidates_ref.py (NEW semantics for configs[4]'s geometric half): per candidate, evaluating only the hole --
+    new-edge dofs from the original field, minus / plus the traction of the airfoil facets whose cell changes -- gives the
+    drag / lift of the fully rebuilt variant mesh to 1e-10 relative."""
+    from oracle import candidates_ref as R
+    from meshdqn_b200.synthetic import synthetic_fields
+    coords, cells, ring_ids = _mesh()
+    base_topo_edges = R.geom.Topology(cells, len(coords)).edges
+    U0, P0 = synthetic_fields(coords, base_topo_edges, T=5, seed=0)
+    base = R.Base(coords, cells, U0, P0, mu=1e-3)
+    assert (base.tags == 1).sum() == len(ring_ids)                       # one airfoil facet per ring vertex
+    rem, _ = C.removable_vertices(coords, cells)
+    d = C.polygon_distance(coords[rem], coords[ring_ids])
+    order = np.nonzero(rem)[0][np.argsort(d)]
+    changed = same = 0
+    for v in list(order[:40]) + list(order[400:410]):                    # first-layer vertices and vertices away from the airfoil
+        cv = cells[(cells == v).any(1)]
+        new = C.retriangulate_star(coords, cv, int(v))
+        if new is None:
+            continue
+        dD, dL, n_eval = R.variant_delta(base, int(v), new)
+        fD, fL = R.variant_full(base, int(v), new)
+        scale = max(np.abs(fD).max(), np.abs(fL).max())
+        assert np.abs(dD - fD).max() <= 1e-10 * scale and np.abs(dL - fL).max() <= 1e-10 * scale, v
+        assert n_eval == len(new) - 1 or len(new) == 1                   # a k-gon hole has k-2 cells and k-3 new diagonals
+        if np.abs(fD - base.drag).max() > 1e-12 * scale:
+            changed += 1
+        else:
+            same += 1
+    assert changed >= 10 and same >= 10       # removals over an airfoil facet change the integral, the others leave it alone
